@@ -1,0 +1,578 @@
+// Pippenger bucket MSM over Pallas / Vesta -- hand-written kernels for sm_100a.
+//
+// What it replaces: ark-ec 0.3 `VariableBaseMSM::multi_scalar_mul` (lambdaclass/openmina_algebra
+// @ 017531e), the inner loop of `accumulator_check` and of the IPA final check under
+// `verify_block` (AL/operator/mina/lib/src/lib.rs:99-111).
+//
+// Design (B200-first, not a translation of the CPU algorithm):
+//   * The SRS is fixed, HBM is 180 GB: keep a table T[w][i] = 2^(c*w) * G_i of affine points resident
+//     (16 x 65536 x 64 B = 64 MiB for Vesta -- it also fits the 126 MB L2).  Every window of every
+//     scalar then lands in ONE shared set of 2^(c-1) signed-digit buckets: no per-window reduction,
+//     no doublings at run time.
+//   * Scalars -> signed c-bit digits -> counting sort by bucket (histogram, scan, scatter) -> one
+//     thread per bucket sums its points with mixed XYZZ additions -> running-sum reduction in
+//     log_m(#buckets) levels -> one affine point.
+//   * A batch of independent MSMs over the same bases (one per proof) runs as one launch set:
+//     bucket id = msm * buckets_per_msm + bucket.
+//   * Arbitrary (non-resident) bases use the same kernels with one bucket set per window and a
+//     final Horner pass (precompute = false).
+// The group law is exact integer arithmetic; the affine output is bit-identical to arkworks'.
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#pragma once
+#include "msm.cuh"
+
+namespace pasta {
+
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                   \
+    } while (0)
+
+static constexpr int MAX_LEVELS = 8;
+
+struct DigitParams {
+    uint32_t n_used;   // scalars per MSM
+    uint32_t n_bases;  // stride of one table window
+    uint32_t nmsm;
+    int c;
+    int W;             // windows per scalar
+    int wsep;          // 1: one bucket set per window (generic bases); 0: shared (precomputed table)
+    uint32_t nbw;      // buckets per window = 2^(c-1)
+};
+
+// bits [pos, pos+c) of a 256-bit little-endian integer (c <= 24)
+__device__ __forceinline__ uint32_t window_bits(const uint32_t s[8], int pos, int c) {
+    int limb = pos >> 5, sh = pos & 31;
+    if (limb >= 8) return 0;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+// Pass 1 (count) and pass 3 (scatter) walk the digits the same way.
+template <bool SCATTER>
+static __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, DigitParams p,
+                                                uint32_t *__restrict__ counters, uint32_t *__restrict__ pairs) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t total = (uint64_t)p.nmsm * p.n_used;
+    if (idx >= total) return;
+    uint32_t m = (uint32_t)(idx / p.n_used);
+    uint32_t i = (uint32_t)(idx % p.n_used);
+    uint32_t s[8];
+    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + idx * 8);
+    uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+    s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    const uint32_t half = 1u << (p.c - 1);
+    uint32_t carry = 0;
+    uint32_t group_base = m * (p.wsep ? (uint32_t)p.W : 1u);
+    for (int w = 0; w < p.W; w++) {
+        uint32_t raw = window_bits(s, w * p.c, p.c) + carry;
+        uint32_t neg = raw > half;
+        uint32_t mag = neg ? (1u << p.c) - raw : raw;
+        carry = neg;
+        if (mag == 0) continue;
+        uint32_t bucket = (group_base + (p.wsep ? (uint32_t)w : 0u)) * p.nbw + (mag - 1u);
+        if (!SCATTER) {
+            atomicAdd(&counters[bucket], 1u);
+        } else {
+            uint32_t pos = atomicAdd(&counters[bucket], 1u);
+            uint32_t entry = p.wsep ? i : (uint32_t)w * p.n_bases + i;
+            pairs[pos] = entry | (neg << 31);
+        }
+    }
+}
+
+// ---- exclusive scan over u32 (three small kernels; inputs are a few 10^4 .. 10^7 counters) --------
+static constexpr int SCAN_THREADS = 1024;
+static constexpr int SCAN_ITEMS = 4;
+static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                             uint32_t *__restrict__ tile_sums, uint32_t n) {
+    __shared__ uint32_t warp_sums[32];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], local = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        local += v[k];
+    }
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (uint32_t)d) wi += t;
+        }
+        warp_sums[lane] = wi - ws;  // exclusive
+        if (lane == 31) tile_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + incl - local;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+// single block: exclusive scan of tile sums in place; writes grand total to tile_sums[ntiles]
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(uint32_t *tile_sums, uint32_t ntiles) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t start = 0; start < ntiles; start += SCAN_THREADS) {
+        uint32_t i = start + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0u, incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= (uint32_t)d) wi += t;
+            }
+            warp_sums[lane] = wi - ws;
+        }
+        __syncthreads();
+        uint32_t carry = carry_s;
+        uint32_t excl = carry + warp_sums[wid] + incl - v;
+        if (i < ntiles) tile_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[ntiles] = carry_s;
+}
+// offsets[i] += tile offset; also writes offsets[n] = total and copies to the scatter cursors
+static __global__ void __launch_bounds__(256) k_scan_finish(uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursors,
+                                                     const uint32_t *__restrict__ tile_sums, uint32_t n, uint32_t ntiles) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint32_t v = offsets[i] + tile_sums[i / SCAN_TILE];
+        offsets[i] = v;
+        cursors[i] = v;
+    } else if (i == n) {
+        offsets[n] = tile_sums[ntiles];
+    }
+}
+
+// ---- bucket accumulation: the dominant kernel ----------------------------------------------------
+// One thread per bucket; the bucket's points are a contiguous run of `pairs`.  Each step gathers one
+// 64-byte affine point (4 x LDG.128, mostly L2 hits: the whole table is 64 MiB) and does one mixed
+// XYZZ addition (10 field multiplications).  The next point is fetched before the current addition
+// so the gather latency hides behind ~1.3k integer instructions.
+template <class F>
+__device__ __forceinline__ affine load_point(const affine *__restrict__ table, uint32_t entry) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(table + (entry & 0x7fffffffu));
+    uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    affine q;
+    q.x.v[0] = a.x; q.x.v[1] = a.y; q.x.v[2] = a.z; q.x.v[3] = a.w;
+    q.x.v[4] = b.x; q.x.v[5] = b.y; q.x.v[6] = b.z; q.x.v[7] = b.w;
+    q.y.v[0] = c.x; q.y.v[1] = c.y; q.y.v[2] = c.z; q.y.v[3] = c.w;
+    q.y.v[4] = d.x; q.y.v[5] = d.y; q.y.v[6] = d.z; q.y.v[7] = d.w;
+    return q;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ pairs,
+                                                    const affine *__restrict__ table, xyzz *__restrict__ buckets,
+                                                    uint32_t nbuckets) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    uint32_t k = offsets[b], end = offsets[b + 1];
+    xyzz acc = Ec<F>::identity();
+    if (k < end) {
+        uint32_t e = pairs[k];
+        affine q = load_point<F>(table, e);
+        for (;;) {
+            uint32_t e_next = 0;
+            affine q_next;
+            bool more = (k + 1 < end);
+            if (more) {
+                e_next = pairs[k + 1];
+                q_next = load_point<F>(table, e_next);
+            }
+            if (e >> 31) q.y = Fd<F>::neg(q.y);
+            Ec<F>::add_mixed(acc, q);
+            if (!more) break;
+            q = q_next;
+            e = e_next;
+            k++;
+        }
+    }
+    buckets[b] = acc;
+}
+
+// ---- running-sum reduction -------------------------------------------------------------------------
+// in: groups x N points.  Thread (g, t) walks m consecutive points from the top:
+//   S = sum_j in[t*m+j],   Wt = sum_j (j+1) * in[t*m+j]
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce_level(const xyzz *__restrict__ in, xyzz *__restrict__ outS,
+                                                      xyzz *__restrict__ outW, uint32_t total_out, int m) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total_out) return;
+    const xyzz *src = in + (size_t)id * m;
+    xyzz run = Ec<F>::identity(), acc = Ec<F>::identity();
+    for (int j = m - 1; j >= 0; j--) {
+        xyzz b = src[j];
+        Ec<F>::add(run, b);
+        Ec<F>::add(acc, run);
+    }
+    outS[id] = run;
+    outW[id] = acc;
+}
+
+// out[g] = sum of in[g*K .. g*K+K): one block per group, strided partial sums then a shared-memory
+// tree whose last five levels run on warp shuffles.
+template <class F>
+__device__ __forceinline__ xyzz shfl_down_point(const xyzz &p, int delta) {
+    xyzz r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], delta);
+        r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], delta);
+        r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], delta);
+        r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], delta);
+    }
+    return r;
+}
+static constexpr int SUM_THREADS = 256;
+template <class F>
+__global__ void __launch_bounds__(SUM_THREADS) k_sum_points(const xyzz *__restrict__ in, xyzz *__restrict__ out, uint32_t K) {
+    __shared__ xyzz warp_part[SUM_THREADS / 32];
+    const xyzz *src = in + (size_t)blockIdx.x * K;
+    xyzz acc = Ec<F>::identity();
+    for (uint32_t i = threadIdx.x; i < K; i += SUM_THREADS) Ec<F>::add(acc, src[i]);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        xyzz o = shfl_down_point<F>(acc, d);
+        Ec<F>::add(acc, o);
+    }
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_part[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        acc = lane < SUM_THREADS / 32 ? warp_part[lane] : Ec<F>::identity();
+#pragma unroll
+        for (int d = 4; d >= 1; d >>= 1) {
+            xyzz o = shfl_down_point<F>(acc, d);
+            Ec<F>::add(acc, o);
+        }
+        if (lane == 0) out[blockIdx.x] = acc;
+    }
+}
+
+struct FinalParams {
+    int levels;
+    int log_m[MAX_LEVELS];  // log2 of the chunk size used at each level
+    int W;                  // windows to Horner-combine per MSM (1 with the precomputed table)
+    int c;
+    uint32_t groups;        // nmsm * W
+};
+// One thread per MSM: unwind the reduction levels, combine windows, normalise to affine.
+//   D_last = sumW[last];  D_l = sumW[l] + m_l * (D_{l+1} - T),  T = sum of all buckets of the group.
+template <class F>
+__global__ void __launch_bounds__(64) k_finalize(const xyzz *__restrict__ sumW /* [levels][groups] */,
+                                                 const xyzz *__restrict__ total /* [groups] */, FinalParams fp,
+                                                 affine *__restrict__ out, uint32_t nmsm) {
+    uint32_t msm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (msm >= nmsm) return;
+    xyzz res = Ec<F>::identity();
+    for (int w = fp.W - 1; w >= 0; w--) {
+        uint32_t g = msm * fp.W + w;
+        xyzz negT = total[g];
+        negT.y = Fd<F>::neg(negT.y);
+        xyzz D = sumW[(size_t)(fp.levels - 1) * fp.groups + g];
+        for (int l = fp.levels - 2; l >= 0; l--) {
+            Ec<F>::add(D, negT);
+            for (int k = 0; k < fp.log_m[l]; k++) D = Ec<F>::dbl(D);
+            Ec<F>::add(D, sumW[(size_t)l * fp.groups + g]);
+        }
+        if (w != fp.W - 1)
+            for (int k = 0; k < fp.c; k++) res = Ec<F>::dbl(res);
+        Ec<F>::add(res, D);
+    }
+    out[msm] = Ec<F>::to_affine(res);
+}
+
+// ---- fixed-base table: T[w] = 2^c * T[w-1], normalised to affine (one Fermat inversion per point) ----
+template <class F>
+__global__ void __launch_bounds__(128) k_table_next(const affine *__restrict__ prev, affine *__restrict__ next, uint32_t n, int c) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xyzz p = Ec<F>::from_affine(prev[i]);
+    for (int k = 0; k < c; k++) p = Ec<F>::dbl(p);
+    next[i] = Ec<F>::to_affine(p);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_affine_to_mont(const uint32_t *__restrict__ in, affine *__restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x, y;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        x.v[k] = in[(size_t)i * 16 + k];
+        y.v[k] = in[(size_t)i * 16 + 8 + k];
+    }
+    affine q;
+    q.x = Fd<F>::to_mont(x);
+    q.y = Fd<F>::to_mont(y);
+    out[i] = q;
+}
+template <class F>
+__global__ void __launch_bounds__(256) k_affine_from_mont(const affine *__restrict__ in, uint32_t *__restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine q = in[i];
+    fe x = Fd<F>::from_mont(q.x), y = Fd<F>::from_mont(q.y);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        out[(size_t)i * 16 + k] = x.v[k];
+        out[(size_t)i * 16 + 8 + k] = y.v[k];
+    }
+}
+
+template <class F>
+void launch_affine_to_mont_t(const uint32_t *d_in, affine *d_out, uint32_t n, cudaStream_t s) {
+    if (n == 0) return;
+    k_affine_to_mont<F><<<(n + 255) / 256, 256, 0, s>>>(d_in, d_out, n);
+}
+template <class F>
+void launch_affine_from_mont_t(const affine *d_in, uint32_t *d_out, uint32_t n, cudaStream_t s) {
+    if (n == 0) return;
+    k_affine_from_mont<F><<<(n + 255) / 256, 256, 0, s>>>(d_in, d_out, n);
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <class F>
+class MsmEngine : public MsmEngineBase {
+   public:
+    ~MsmEngine() override { release(); }
+
+    void set_bases(const affine *d_bases, uint32_t n, const MsmConfig &cfg, cudaStream_t s) override {
+        if (cfg.c < 2 || cfg.c > 20) throw std::runtime_error("msm: window bits out of range");
+        if (cfg.leaf < 2 || (cfg.leaf & (cfg.leaf - 1))) throw std::runtime_error("msm: leaf must be a power of two");
+        free_dev(table_own_);
+        cfg_ = cfg;
+        n_bases_ = n;
+        W_ = 255 / cfg.c + 1;
+        nbw_ = 1u << (cfg.c - 1);
+        if (cfg.precompute) {
+            if ((uint64_t)W_ * n >= (1ull << 31)) throw std::runtime_error("msm: table too large for 31-bit entries");
+            CUDA_OK(cudaMalloc(&table_own_, (size_t)W_ * n * sizeof(affine)));
+            CUDA_OK(cudaMemcpyAsync(table_own_, d_bases, (size_t)n * sizeof(affine), cudaMemcpyDeviceToDevice, s));
+            for (int w = 1; w < W_; w++)
+                k_table_next<F><<<(n + 127) / 128, 128, 0, s>>>(table_own_ + (size_t)(w - 1) * n, table_own_ + (size_t)w * n, n, cfg.c);
+            CUDA_OK(cudaGetLastError());
+            table_ = table_own_;
+        } else {
+            if (n >= (1u << 31)) throw std::runtime_error("msm: too many bases");
+            table_ = d_bases;
+        }
+        // reduction plan
+        levels_ = 0;
+        uint32_t N = nbw_;
+        while (N > 1) {
+            int m = cfg.leaf;
+            while ((uint32_t)m > N) m >>= 1;
+            int lg = 0;
+            while ((1 << lg) < m) lg++;
+            if (levels_ >= MAX_LEVELS) throw std::runtime_error("msm: too many reduction levels");
+            log_m_[levels_++] = lg;
+            N /= m;
+        }
+        if (levels_ == 0) {  // c == 1: a single bucket
+            log_m_[0] = 0;
+            levels_ = 1;
+        }
+    }
+
+    void run(const uint32_t *d_scalars, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) override {
+        if (!table_) throw std::runtime_error("msm: no bases set");
+        if (n_used > n_bases_) throw std::runtime_error("msm: n_used exceeds resident bases");
+        if (nmsm == 0) return;
+        const uint32_t groups_per_msm = cfg_.precompute ? 1u : (uint32_t)W_;
+        const uint64_t buckets_per_msm = (uint64_t)groups_per_msm * nbw_;
+        const uint64_t pairs_per_msm = (uint64_t)n_used * W_;
+        // chunk the batch so the workspace stays bounded
+        uint64_t chunk = nmsm;
+        const uint64_t max_buckets = 1ull << 23, max_pairs = 1ull << 28;
+        if (chunk * buckets_per_msm > max_buckets) chunk = max_buckets / buckets_per_msm;
+        if (pairs_per_msm && chunk * pairs_per_msm > max_pairs) chunk = max_pairs / pairs_per_msm;
+        if (chunk == 0) chunk = 1;
+        if (chunk * buckets_per_msm >= (1ull << 32) || chunk * pairs_per_msm >= (1ull << 32))
+            throw std::runtime_error("msm: problem too large for 32-bit indices");
+        ensure_workspace((uint32_t)chunk, n_used);
+        for (uint32_t done = 0; done < nmsm; done += (uint32_t)chunk) {
+            uint32_t cur = (uint32_t)std::min<uint64_t>(chunk, nmsm - done);
+            run_chunk(d_scalars + (size_t)done * n_used * 8, cur, n_used, d_out + done, s);
+        }
+    }
+
+    size_t workspace_bytes() const override { return ws_bytes_ + (table_own_ ? (size_t)W_ * n_bases_ * sizeof(affine) : 0); }
+    int launches_per_run() const override { return 5 + 2 * levels_ + 1; }
+    void enable_kernel_timing(bool on) override {
+        timing_ = on;
+        if (on && !ev0_) {
+            CUDA_OK(cudaEventCreate(&ev0_));
+            CUDA_OK(cudaEventCreate(&ev1_));
+        }
+    }
+    float last_accumulate_ms() override {
+        if (!timing_ || !ev0_) return 0.f;
+        float ms = 0.f;
+        CUDA_OK(cudaEventSynchronize(ev1_));
+        CUDA_OK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        return ms;
+    }
+
+   private:
+    template <class T>
+    static void free_dev(T *&p) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+    void release() {
+        free_dev(table_own_);
+        free_dev(counters_);
+        free_dev(offsets_);
+        free_dev(tile_sums_);
+        free_dev(pairs_);
+        free_dev(buckets_);
+        free_dev(lvlS_[0]);
+        free_dev(lvlS_[1]);
+        free_dev(lvlW_);
+        free_dev(sumW_);
+        if (ev0_) cudaEventDestroy(ev0_);
+        if (ev1_) cudaEventDestroy(ev1_);
+        ev0_ = ev1_ = nullptr;
+    }
+
+    void ensure_workspace(uint32_t nmsm, uint32_t n_used) {
+        const uint32_t groups = nmsm * (cfg_.precompute ? 1u : (uint32_t)W_);
+        const uint64_t nb = (uint64_t)groups * nbw_;
+        const uint64_t np = (uint64_t)nmsm * n_used * W_;
+        if (nb <= cap_buckets_ && np <= cap_pairs_ && groups <= cap_groups_) return;
+        free_dev(counters_);
+        free_dev(offsets_);
+        free_dev(tile_sums_);
+        free_dev(pairs_);
+        free_dev(buckets_);
+        free_dev(lvlS_[0]);
+        free_dev(lvlS_[1]);
+        free_dev(lvlW_);
+        free_dev(sumW_);
+        cap_buckets_ = std::max<uint64_t>(nb, cap_buckets_);
+        cap_pairs_ = std::max<uint64_t>(np, cap_pairs_);
+        cap_groups_ = std::max<uint32_t>(groups, cap_groups_);
+        size_t ntiles = (cap_buckets_ + SCAN_TILE - 1) / SCAN_TILE;
+        size_t first = (cap_buckets_ >> log_m_[0]) + 1;
+        ws_bytes_ = 0;
+        auto alloc = [&](auto &ptr, size_t bytes) {
+            CUDA_OK(cudaMalloc(&ptr, bytes));
+            ws_bytes_ += bytes;
+        };
+        alloc(counters_, (cap_buckets_ + 1) * sizeof(uint32_t));
+        alloc(offsets_, (cap_buckets_ + 1) * sizeof(uint32_t));
+        alloc(tile_sums_, (ntiles + 1) * sizeof(uint32_t));
+        alloc(pairs_, std::max<uint64_t>(cap_pairs_, 1) * sizeof(uint32_t));
+        alloc(buckets_, cap_buckets_ * sizeof(xyzz));
+        alloc(lvlS_[0], first * sizeof(xyzz));
+        alloc(lvlS_[1], first * sizeof(xyzz));
+        alloc(lvlW_, first * sizeof(xyzz));
+        alloc(sumW_, (size_t)MAX_LEVELS * cap_groups_ * sizeof(xyzz));
+    }
+
+    void run_chunk(const uint32_t *d_scalars, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) {
+        DigitParams dp;
+        dp.n_used = n_used;
+        dp.n_bases = n_bases_;
+        dp.nmsm = nmsm;
+        dp.c = cfg_.c;
+        dp.W = W_;
+        dp.wsep = cfg_.precompute ? 0 : 1;
+        dp.nbw = nbw_;
+        const uint32_t groups = nmsm * (cfg_.precompute ? 1u : (uint32_t)W_);
+        const uint32_t nb = groups * nbw_;
+        const uint64_t nscal = (uint64_t)nmsm * n_used;
+        const uint32_t dblocks = (uint32_t)((nscal + 255) / 256);
+        const uint32_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
+
+        CUDA_OK(cudaMemsetAsync(counters_, 0, (size_t)(nb + 1) * sizeof(uint32_t), s));
+        if (dblocks) k_digits<false><<<dblocks, 256, 0, s>>>(d_scalars, dp, counters_, nullptr);
+        k_scan_tiles<<<ntiles, SCAN_THREADS, 0, s>>>(counters_, offsets_, tile_sums_, nb);
+        k_scan_top<<<1, SCAN_THREADS, 0, s>>>(tile_sums_, ntiles);
+        k_scan_finish<<<(nb + 1 + 255) / 256, 256, 0, s>>>(offsets_, counters_, tile_sums_, nb, ntiles);
+        if (dblocks) k_digits<true><<<dblocks, 256, 0, s>>>(d_scalars, dp, counters_, pairs_);
+        if (timing_) CUDA_OK(cudaEventRecord(ev0_, s));
+        k_accumulate<F><<<(nb + 127) / 128, 128, 0, s>>>(offsets_, pairs_, table_, buckets_, nb);
+        if (timing_) CUDA_OK(cudaEventRecord(ev1_, s));
+
+        // running-sum levels
+        const xyzz *in = buckets_;
+        uint32_t N = nbw_;
+        xyzz *last_S = nullptr;
+        for (int l = 0; l < levels_; l++) {
+            int m = 1 << log_m_[l];
+            uint32_t outN = N / m;
+            uint32_t total_out = groups * outN;
+            xyzz *S = lvlS_[l & 1];
+            k_reduce_level<F><<<(total_out + 127) / 128, 128, 0, s>>>(in, S, lvlW_, total_out, m);
+            k_sum_points<F><<<groups, SUM_THREADS, 0, s>>>(lvlW_, sumW_ + (size_t)l * groups, outN);
+            in = S;
+            last_S = S;
+            N = outN;
+        }
+        FinalParams fp;
+        fp.levels = levels_;
+        for (int l = 0; l < MAX_LEVELS; l++) fp.log_m[l] = l < levels_ ? log_m_[l] : 0;
+        fp.W = cfg_.precompute ? 1 : W_;
+        fp.c = cfg_.c;
+        fp.groups = groups;
+        k_finalize<F><<<(nmsm + 63) / 64, 64, 0, s>>>(sumW_, last_S, fp, d_out, nmsm);
+        CUDA_OK(cudaGetLastError());
+    }
+
+    MsmConfig cfg_;
+    uint32_t n_bases_ = 0, nbw_ = 0;
+    int W_ = 0, levels_ = 0;
+    int log_m_[MAX_LEVELS] = {0};
+    const affine *table_ = nullptr;
+    affine *table_own_ = nullptr;
+    uint32_t *counters_ = nullptr, *offsets_ = nullptr, *tile_sums_ = nullptr, *pairs_ = nullptr;
+    xyzz *buckets_ = nullptr, *lvlS_[2] = {nullptr, nullptr}, *lvlW_ = nullptr, *sumW_ = nullptr;
+    uint64_t cap_buckets_ = 0, cap_pairs_ = 0;
+    uint32_t cap_groups_ = 0;
+    size_t ws_bytes_ = 0;
+    bool timing_ = false;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+};
+
+}  // namespace pasta

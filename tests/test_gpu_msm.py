@@ -1,0 +1,152 @@
+"""GPU tier: the CUDA path, called through the C ABI, against the oracle (bit-exact)."""
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+from oracle import cref, pasta
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+MOD = {0: pasta.P, 1: pasta.Q}          # coordinate field of curve id
+SCALAR_MOD = {0: pasta.Q, 1: pasta.P}   # scalar field of curve id
+DEPTH = {0: 32768, 1: 65536}
+
+
+def rand_scalars(rng, n, m):
+    return cref.ints_to_bytes([rng.randrange(m) for _ in range(n)])
+
+
+def test_device_field_ops(gpu):
+    rng = random.Random(1)
+    for fid, m in ((0, pasta.P), (1, pasta.Q)):
+        a = [rng.randrange(m) for _ in range(2000)] + [0, 1, m - 1, m - 1, 2]
+        b = [rng.randrange(m) for _ in range(2000)] + [m - 1, m - 1, m - 1, 1, (m + 1) // 2]
+        A, B = cref.ints_to_bytes(a), cref.ints_to_bytes(b)
+        assert gpu.field_op(fid, 0, A, B) == cref.ints_to_bytes([x * y % m for x, y in zip(a, b)])
+        assert gpu.field_op(fid, 1, A, B) == cref.ints_to_bytes([(x + y) % m for x, y in zip(a, b)])
+        assert gpu.field_op(fid, 2, A, B) == cref.ints_to_bytes([(x - y) % m for x, y in zip(a, b)])
+        assert gpu.field_op(fid, 4, A) == cref.ints_to_bytes([x * x % m for x in a])
+        assert gpu.field_op(fid, 3, A[: 32 * 64]) == cref.ints_to_bytes([pow(x, -1, m) for x in a[:64]])
+
+
+def test_device_srs_is_the_reference_srs(gpu):
+    pins = json.load(open(os.path.join(GOLDEN, "srs_sha256.json")))
+    g, h = gpu.srs_points(1, 0, 65536, True)
+    assert hashlib.sha256(g).hexdigest() == pins["vesta"]["sha256_g_65536"] and h.hex() == pins["vesta"]["h"]
+    g, h = gpu.srs_points(0, 0, 32768, True)
+    assert hashlib.sha256(g).hexdigest() == pins["pallas"]["sha256_g_32768"] and h.hex() == pins["pallas"]["h"]
+
+
+def test_device_point_add_including_special_cases(gpu):
+    for cid in (0, 1):
+        m = MOD[cid]
+        pts = gpu.srs_points(cid, 0, 64)
+        P = [cref.bytes_to_point(pts[64 * i : 64 * i + 64]) for i in range(64)]
+        a = list(P)
+        b = P[1:] + P[:1]
+        # doubling, cancellation and identities (even index = mixed formula, odd = full formula)
+        a += [P[3], P[3], P[4], P[4], None, None, P[5], P[5], None, None]
+        b += [P[3], P[3], pasta.neg(P[4], m), pasta.neg(P[4], m), P[6], P[6], None, None, None, None]
+        got = gpu.point_add(cid, cref.points_to_bytes(a), cref.points_to_bytes(b))
+        want = cref.points_to_bytes([pasta.add(x, y, m) for x, y in zip(a, b)])
+        assert got == want
+
+
+@pytest.mark.parametrize("cid", [0, 1])
+@pytest.mark.parametrize("n", [1, 2, 33, 1000, 4097])
+def test_msm_srs_small_random(gpu, cid, n):
+    rng = random.Random(100 + n)
+    sc = rand_scalars(rng, n, SCALAR_MOD[cid])
+    pts = gpu.srs_points(cid, 0, n)
+    want, inf = cref.msm(cid, sc, pts, 4)
+    (got,) = gpu.msm_srs(cid, sc, n)
+    assert got == want and not inf
+
+
+@pytest.mark.parametrize("cid", [0, 1])
+def test_msm_srs_edge_scalars(gpu, cid):
+    m = SCALAR_MOD[cid]
+    n = 513
+    pts = gpu.srs_points(cid, 0, n)
+    rng = random.Random(9)
+    cases = {
+        "zeros": [0] * n,
+        "ones": [1] * n,
+        "minus_one": [m - 1] * n,
+        "window_boundaries": [(1 << (16 * (i % 16))) % m for i in range(n)],
+        "half_digits": [int("8000" * 15, 16) % m] * n,   # every 16-bit digit = 2^15 (signed-digit edge)
+        "ffff_digits": [((1 << 254) - 1) % m] * n,
+        "mixed": [rng.choice([0, 1, m - 1, rng.randrange(m)]) for _ in range(n)],
+    }
+    for name, sc in cases.items():
+        scb = cref.ints_to_bytes(sc)
+        want, inf = cref.msm(cid, scb, pts, 4)
+        (got,) = gpu.msm_srs(cid, scb, n)
+        assert got == want, name
+    # cancelling pair -> identity: s*G0 + (m-s)*G0 needs generic bases
+    s = rng.randrange(m)
+    two = pts[:64] * 2
+    got = gpu.msm(cid, cref.ints_to_bytes([s, m - s]), two)
+    assert got == b"\0" * 64
+
+
+def test_msm_empty(gpu):
+    assert gpu.msm(1, b"", b"") == b"\0" * 64
+
+
+@pytest.mark.parametrize("cid", [0, 1])
+def test_msm_batch_of_independent_msms(gpu, cid):
+    rng = random.Random(77)
+    n, nmsm = 2048, 5
+    pts = gpu.srs_points(cid, 0, n)
+    sc = [rand_scalars(rng, n, SCALAR_MOD[cid]) for _ in range(nmsm)]
+    got = gpu.msm_srs(cid, b"".join(sc), n)
+    for k in range(nmsm):
+        want, _ = cref.msm(cid, sc[k], pts, 4)
+        assert got[k] == want
+
+
+@pytest.mark.parametrize("cid", [0, 1])
+@pytest.mark.parametrize("c", [0, 7, 13, 16])
+def test_msm_generic_bases_windows(gpu, cid, c):
+    rng = random.Random(31 + c)
+    n = 3000
+    # bases with repeats (forces the doubling branch inside buckets) and an identity
+    base = gpu.srs_points(cid, 100, 500)
+    pts = b"".join(base[64 * (i % 500) : 64 * (i % 500) + 64] for i in range(n - 1)) + b"\0" * 64
+    sc = rand_scalars(rng, n, SCALAR_MOD[cid])
+    want, _ = cref.msm(cid, sc, pts, 4)
+    assert gpu.msm(cid, sc, pts, c) == want
+
+
+def test_accumulator_kats_on_gpu(gpu, state_proof):
+    # K-A, K-B, K-C through the CUDA path (scalars prepared by the oracle here; the device
+    # b_poly/endo kernels have their own tests)
+    pr = state_proof["candidate_tip_proof"]
+    pre = b"".join(x.to_bytes(16, "little") for x in pr["bulletproof_challenges"])
+    s = cref.bpoly_coeffs(cref.FP, cref.endo_to_field(cref.FP, pre, pasta.ENDO_FP))
+    (got,) = gpu.msm_srs(1, s, 65536)
+    assert cref.bytes_to_point(got) == pr["wrap_challenge_polynomial_commitment"]
+    for k in range(2):
+        pre = b"".join(x.to_bytes(16, "little") for x in pr["wrap_old_bulletproof_challenges"][k])
+        s = cref.bpoly_coeffs(cref.FQ, cref.endo_to_field(cref.FQ, pre, pasta.ENDO_FQ))
+        (got,) = gpu.msm_srs(0, s, 32768)
+        assert cref.bytes_to_point(got) == pr["step_challenge_polynomial_commitments"][k]
+
+
+def test_msm_full_depth_random_and_linearity(gpu):
+    # full SRS depth vs the oracle, plus a size-independent property: MSM(a) + MSM(b) == MSM(a+b)
+    rng = random.Random(2024)
+    for cid in (0, 1):
+        n, m, fm = DEPTH[cid], SCALAR_MOD[cid], MOD[cid]
+        a = [rng.randrange(m) for _ in range(n)]
+        b = [rng.randrange(m) for _ in range(n)]
+        ab = [(x + y) % m for x, y in zip(a, b)]
+        ra, rb, rab = gpu.msm_srs(cid, cref.ints_to_bytes(a) + cref.ints_to_bytes(b) + cref.ints_to_bytes(ab), n)
+        want, _ = cref.msm(cid, cref.ints_to_bytes(a), gpu.srs_points(cid, 0, n), 8)
+        assert ra == want
+        assert pasta.add(cref.bytes_to_point(ra), cref.bytes_to_point(rb), fm) == cref.bytes_to_point(rab)
