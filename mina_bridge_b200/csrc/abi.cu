@@ -240,6 +240,34 @@ template <class F>
 __global__ void k_field_op(int op, uint32_t n, const fe *a, const fe *b, fe *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (op >= 10) {  // raw (no Montgomery conversion) variants for debugging the PTX path
+        fe r0;
+        switch (op) {
+            case 10: r0 = Fd<F>::mul(a[i], b[i]); break;
+            case 11: r0 = Fd<F>::mul_portable(a[i], b[i]); break;
+            case 12: r0 = Fd<F>::add(a[i], b[i]); break;
+            case 13: r0 = Fd<F>::sub(a[i], b[i]); break;
+            case 14: r0 = Fd<F>::add_portable(a[i], b[i]); break;
+            case 15: r0 = Fd<F>::sub_portable(a[i], b[i]); break;
+#ifdef __CUDA_ARCH__
+            case 20: case 21: {
+                uint32_t U[16];
+                Fd<F>::mul_wide(U, a[i], b[i]);
+                for (int k = 0; k < 8; k++) r0.v[k] = U[(op == 20 ? 0 : 8) + k];
+                break;
+            }
+            case 22: {
+                uint32_t U[16];
+                for (int k = 0; k < 8; k++) { U[k] = a[i].v[k]; U[8 + k] = b[i].v[k]; }
+                r0 = Fd<F>::redc(U);
+                break;
+            }
+#endif
+            default: r0 = fe_zero(); break;
+        }
+        out[i] = r0;
+        return;
+    }
     fe x = Fd<F>::to_mont(a[i]);
     fe y = Fd<F>::to_mont(b[i]);
     fe r;
@@ -276,7 +304,7 @@ extern "C" {
 int mina_b200_field_op(int field, int op, uint32_t n, const uint8_t *a32, const uint8_t *b32, uint8_t *out32) {
     ABI_TRY
     require_ready();
-    if (field < 0 || field > 1 || op < 0 || op > 4) throw std::runtime_error("bad field/op");
+    if (field < 0 || field > 1 || op < 0 || op > 22) throw std::runtime_error("bad field/op");
     if (n == 0) return 0;
     Context &c = ctx();
     std::lock_guard<std::mutex> lk(c.mu);

@@ -81,7 +81,7 @@ struct Fd {
         return r;
     }
 
-    PASTA_HD static fe add(const fe &a, const fe &b) {
+    PASTA_HD static fe add_portable(const fe &a, const fe &b) {
         fe s;
         uint32_t c = 0;
 #pragma unroll
@@ -92,9 +92,8 @@ struct Fd {
         }
         return reduce_once(s, c);  // p < 2^255 so c is always 0; kept for clarity
     }
-    PASTA_HD static fe dbl(const fe &a) { return add(a, a); }
 
-    PASTA_HD static fe sub(const fe &a, const fe &b) {
+    PASTA_HD static fe sub_portable(const fe &a, const fe &b) {
         fe d;
         uint32_t borrow = 0;
 #pragma unroll
@@ -113,7 +112,6 @@ struct Fd {
         }
         return r;
     }
-    PASTA_HD static fe neg(const fe &a) { return sub(fe_zero(), a); }
 
     // Portable CIOS Montgomery product (host and device); the reference implementation the
     // PTX path below is tested against.
@@ -152,9 +150,249 @@ struct Fd {
         return reduce_once(r, t[8]);
     }
 
+#ifdef __CUDA_ARCH__
+    // ---- sm_100a path ---------------------------------------------------------------------------
+    // acc[0..8] += (a0, a1, a2, a3) * b: four 64-bit products on aligned register pairs, one carry
+    // chain (each mad.lo.cc/madc.hi.cc pair fuses into one IMAD.WIDE.U32.X), carry into acc[8].
+    static __device__ __forceinline__ void mad_row(uint32_t *acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                   uint32_t b) {
+        asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+              "+r"(acc[7]), "+r"(acc[8])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+    }
+    // same, into fresh registers (acc[0..8) = products, no carry limb)
+    static __device__ __forceinline__ void mul_row(uint32_t *acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                   uint32_t b) {
+        asm("mul.lo.u32 %0, %8, %12;\n\t"
+            "mul.hi.u32 %1, %8, %12;\n\t"
+            "mul.lo.u32 %2, %9, %12;\n\t"
+            "mul.hi.u32 %3, %9, %12;\n\t"
+            "mul.lo.u32 %4, %10, %12;\n\t"
+            "mul.hi.u32 %5, %10, %12;\n\t"
+            "mul.lo.u32 %6, %11, %12;\n\t"
+            "mul.hi.u32 %7, %11, %12;"
+            : "=&r"(acc[0]), "=&r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5]), "=&r"(acc[6]),
+              "=&r"(acc[7])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+    }
 
-    PASTA_HD static fe mul(const fe &a, const fe &b) { return mul_portable(a, b); }
+    // One Montgomery round on the window U[i..i+4]:  m = -U[i];  U += m * (1, t1, t2, t3) << 32i.
+    // `d` carries the deferred carry that belongs to limb i+4 in and the one for limb i+5 out.
+    static __device__ __forceinline__ uint32_t redc_round(uint32_t u0, uint32_t &u1, uint32_t &u2, uint32_t &u3,
+                                                          uint32_t &u4, uint32_t &d) {
+        uint32_t m, scratch;
+        asm("sub.u32 %0, 0, %7;\n\t"
+            "add.cc.u32 %1, %7, %0;\n\t"       // CF = (u0 != 0)
+            "madc.lo.cc.u32 %2, %0, %8, %2;\n\t"
+            "madc.lo.cc.u32 %3, %0, %9, %3;\n\t"
+            "madc.lo.cc.u32 %4, %0, %10, %4;\n\t"
+            "addc.cc.u32 %5, %5, %6;\n\t"
+            "addc.u32 %6, 0, 0;\n\t"
+            "mad.hi.cc.u32 %3, %0, %8, %3;\n\t"
+            "madc.hi.cc.u32 %4, %0, %9, %4;\n\t"
+            "madc.hi.cc.u32 %5, %0, %10, %5;\n\t"
+            "addc.u32 %6, %6, 0;"
+            : "=&r"(m), "=&r"(scratch), "+r"(u1), "+r"(u2), "+r"(u3), "+r"(u4), "+r"(d)
+            : "r"(u0), "r"(F::MOD(1)), "r"(F::MOD(2)), "r"(F::MOD(3)));
+        return m;
+    }
+
+    static __device__ __forceinline__ fe cond_sub_p(const uint32_t *r) {
+        // r < 2p < 2^256: subtract p once if r >= p
+        uint32_t d[8], borrow;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7]),
+              "=&r"(borrow)
+            : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+              "r"(F::MOD(0)), "r"(F::MOD(1)), "r"(F::MOD(2)), "r"(F::MOD(3)), "r"(F::MOD(4)), "r"(F::MOD(5)),
+              "r"(F::MOD(6)), "r"(F::MOD(7)));
+        fe o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.v[i] = borrow ? r[i] : d[i];
+        return o;
+    }
+
+    static __device__ __forceinline__ fe mul_ptx(const fe &a, const fe &b) {
+        uint32_t U[16];
+        mul_wide(U, a, b);
+        return redc(U);
+    }
+    static __device__ __forceinline__ void mul_wide(uint32_t *U, const fe &a, const fe &b) {
+        // 512-bit product: X collects a_j*b_i with i+j even, Y those with i+j odd (stored one limb down)
+        uint32_t X[17], Y[17];
+#pragma unroll
+        for (int i = 8; i < 17; i++) X[i] = Y[i] = 0;
+        mul_row(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+        mul_row(Y, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            if (i & 1) {
+                mad_row(&Y[i - 1], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+                mad_row(&X[i + 1], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+            } else {
+                mad_row(&X[i], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+                mad_row(&Y[i], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+            }
+        }
+        U[0] = X[0];
+        asm("add.cc.u32 %0, %15, %30;\n\t"
+            "addc.cc.u32 %1, %16, %31;\n\t"
+            "addc.cc.u32 %2, %17, %32;\n\t"
+            "addc.cc.u32 %3, %18, %33;\n\t"
+            "addc.cc.u32 %4, %19, %34;\n\t"
+            "addc.cc.u32 %5, %20, %35;\n\t"
+            "addc.cc.u32 %6, %21, %36;\n\t"
+            "addc.cc.u32 %7, %22, %37;\n\t"
+            "addc.cc.u32 %8, %23, %38;\n\t"
+            "addc.cc.u32 %9, %24, %39;\n\t"
+            "addc.cc.u32 %10, %25, %40;\n\t"
+            "addc.cc.u32 %11, %26, %41;\n\t"
+            "addc.cc.u32 %12, %27, %42;\n\t"
+            "addc.cc.u32 %13, %28, %43;\n\t"
+            "addc.u32 %14, %29, %44;"
+            : "=&r"(U[1]), "=&r"(U[2]), "=&r"(U[3]), "=&r"(U[4]), "=&r"(U[5]), "=&r"(U[6]), "=&r"(U[7]), "=&r"(U[8]),
+              "=&r"(U[9]), "=&r"(U[10]), "=&r"(U[11]), "=&r"(U[12]), "=&r"(U[13]), "=&r"(U[14]), "=&r"(U[15])
+            : "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]), "r"(X[8]), "r"(X[9]),
+              "r"(X[10]), "r"(X[11]), "r"(X[12]), "r"(X[13]), "r"(X[14]), "r"(X[15]), "r"(Y[0]), "r"(Y[1]),
+              "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]), "r"(Y[8]), "r"(Y[9]), "r"(Y[10]),
+              "r"(Y[11]), "r"(Y[12]), "r"(Y[13]), "r"(Y[14]));
+    }
+
+    // Montgomery reduction of a 512-bit value U < p * 2^256 (consumes U).
+    static __device__ __forceinline__ fe redc(uint32_t *U) {
+        uint32_t m[8], d = 0, d7;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            m[i] = redc_round(U[i], U[i + 1], U[i + 2], U[i + 3], U[i + 4], d);
+            if (i == 0) {
+                // The 2^254 part of p: (m0 << 30) lands in limb 7 and must be there before round 7.
+                // The carry is taken by comparison on purpose: with add.cc here, ptxas 12.9 fuses
+                // neg + shl + add.cc into `LEA RZ, P, -R, R, 0x1e`, whose carry-out is wrong
+                // whenever m0 = 0 (mod 4).
+                uint32_t s30 = m[0] << 30;
+                U[7] += s30;
+                d7 = U[7] < s30 ? 1u : 0u;
+            }
+        }
+        // limbs 0..7 are now zero.  result = U[8..16) + (m >> 2) + d7 (limb 8) + d (limb 12)
+        uint32_t sh[8];
+#pragma unroll
+        for (int k = 0; k < 7; k++) sh[k] = __funnelshift_r(m[k], m[k + 1], 2);
+        sh[7] = m[7] >> 2;
+        uint32_t r[8];
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;\n\t"
+            "add.cc.u32 %0, %0, %24;\n\t"
+            "addc.cc.u32 %1, %1, 0;\n\t"
+            "addc.cc.u32 %2, %2, 0;\n\t"
+            "addc.cc.u32 %3, %3, 0;\n\t"
+            "addc.cc.u32 %4, %4, %25;\n\t"
+            "addc.cc.u32 %5, %5, 0;\n\t"
+            "addc.cc.u32 %6, %6, 0;\n\t"
+            "addc.u32 %7, %7, 0;"
+            : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+            : "r"(U[8]), "r"(U[9]), "r"(U[10]), "r"(U[11]), "r"(U[12]), "r"(U[13]), "r"(U[14]), "r"(U[15]),
+              "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]), "r"(sh[4]), "r"(sh[5]), "r"(sh[6]), "r"(sh[7]),
+              "r"(d7), "r"(d));
+        return cond_sub_p(r);
+    }
+
+    static __device__ __forceinline__ fe add_ptx(const fe &a, const fe &b) {
+        uint32_t r[8];
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+              "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        return cond_sub_p(r);
+    }
+    static __device__ __forceinline__ fe sub_ptx(const fe &a, const fe &b) {
+        uint32_t d[8], borrow;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7]),
+              "=&r"(borrow)
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+              "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        // borrow is 0 or 0xffffffff: add p back under the mask
+        fe o;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=&r"(o.v[0]), "=&r"(o.v[1]), "=&r"(o.v[2]), "=&r"(o.v[3]), "=&r"(o.v[4]), "=&r"(o.v[5]), "=&r"(o.v[6]),
+              "=&r"(o.v[7])
+            : "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]),
+              "r"(F::MOD(0) & borrow), "r"(F::MOD(1) & borrow), "r"(F::MOD(2) & borrow), "r"(F::MOD(3) & borrow),
+              "r"(F::MOD(4) & borrow), "r"(F::MOD(5) & borrow), "r"(F::MOD(6) & borrow), "r"(F::MOD(7) & borrow));
+        return o;
+    }
+#endif
+
+    PASTA_HD static fe mul(const fe &a, const fe &b) {
+#ifdef __CUDA_ARCH__
+        return mul_ptx(a, b);
+#else
+        return mul_portable(a, b);
+#endif
+    }
     PASTA_HD static fe sqr(const fe &a) { return mul(a, a); }
+    PASTA_HD static fe add(const fe &a, const fe &b) {
+#ifdef __CUDA_ARCH__
+        return add_ptx(a, b);
+#else
+        return add_portable(a, b);
+#endif
+    }
+    PASTA_HD static fe sub(const fe &a, const fe &b) {
+#ifdef __CUDA_ARCH__
+        return sub_ptx(a, b);
+#else
+        return sub_portable(a, b);
+#endif
+    }
+    PASTA_HD static fe dbl(const fe &a) { return add(a, a); }
+    PASTA_HD static fe neg(const fe &a) { return sub(fe_zero(), a); }
 
     PASTA_HD static fe to_mont(const fe &a) { return mul(a, constant_r2()); }
     PASTA_HD static fe from_mont(const fe &a) {
