@@ -12,8 +12,13 @@
  * AL/operator/mina_account/lib/src/merkle_verifier.rs:27.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg load this library.  The
- * shipped verifier never links it.  Parity: pinned against the accumulator KATs in
+ * shipped verifier never links it.
+ *
+ * Parity: field/curve/MSM/b_poly/endo/SRS routines are PINNED against the accumulator KATs in
  * tests/golden/mina_state.proof and against srs/{vesta,pallas}.srs (tests/test_oracle_kats.py).
+ * oracle_poseidon_permute is PARITY UNPINNED: it takes the MDS + round constants as data and no
+ * table that passes the reference's known-answer test (merkle_verifier.rs:43-58) is available
+ * here -- see DESIGN.md section 0.  The reference binary itself was never run (unbuildable here).
  *
  * All field elements cross the ABI as 32-byte little-endian canonical integers.
  */
