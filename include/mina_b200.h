@@ -8,8 +8,8 @@
  *   verify_account_inclusion_ffi (AL/operator/mina_account/lib/src/lib.rs:16-78,
  *                                 header AL/operator/mina_account/lib/mina_account_verifier.h:3-6,
  *                                 cgo caller AL/operator/mina_account/mina_account.go:27-32)
- * are declared in mina_verifier.h / mina_account_verifier.h next to this file with the reference's
- * exact signatures.  Everything below is ADDITIVE: lifecycle, batch entry points and the individual
+ * are declared in include/mina_verifier.h and include/mina_account_verifier.h with the reference's
+ * signatures.  Everything below is ADDITIVE: lifecycle, per-stage reports, and the individual
  * hot-path kernels (MSM, IPA scalar helpers, Poseidon) exposed for parity tests and benchmarks.
  *
  * Conventions: plain pointers and sizes only.  Field elements are 32-byte little-endian canonical
@@ -36,10 +36,14 @@ extern "C" {
 #define MINA_B200_FIELD_FQ 1
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
-/* Select `device`, build (or load from `cache_dir`, may be NULL) the two SRS, upload them and build
- * the fixed-base MSM tables.  Mirrors the reference's lazy statics MINA_SRS / *_VERIFIER_INDEX
- * (AL/operator/mina/lib/src/lib.rs:23-35).  Idempotent; thread-safe. */
-int mina_b200_init(int device, const char *cache_dir);
+/* Select `device`; load the two SRS from `data_dir` (derive them by hash-to-curve when the cache is
+ * missing or does not match the digest compiled into the library), upload them, build the fixed-base
+ * MSM tables, load the verification keys (<data_dir>/{devnet,mainnet}_vk.json) and, when present and
+ * passing the reference's known-answer test, the Poseidon tables.  Mirrors the reference's lazy
+ * statics MINA_SRS / *_VERIFIER_INDEX (AL/operator/mina/lib/src/lib.rs:23-35).  `data_dir` NULL =
+ * $MINA_B200_DATA_DIR, else the `data` directory next to the shared object.  Idempotent for the same
+ * device; an error for a different one.  Thread-safe. */
+int mina_b200_init(int device, const char *data_dir);
 void mina_b200_shutdown(void);
 const char *mina_b200_last_error(void);
 /* Number of kernels launched by this library since init (the `gpu_launches` claim of bench.py). */
@@ -57,16 +61,73 @@ int mina_b200_msm_srs(int curve, uint32_t nmsm, uint32_t n, const uint8_t *scala
 /* One MSM over caller-supplied bases (host buffers, canonical affine).  window_bits 0 = default. */
 int mina_b200_msm(int curve, uint32_t n, const uint8_t *scalars32, const uint8_t *points64, int window_bits,
                   uint8_t *out64);
-/* Device-resident variant used by bench.py's `value` leg: d_scalars is a CUDA device pointer to
- * nmsm*n*8 uint32 (canonical), d_out64 a device pointer to nmsm*16 uint32 (canonical affine).
- * Work is enqueued on `cuda_stream` (a cudaStream_t passed as void*); no synchronisation.
- * If `accumulate_ms` is non-NULL the call synchronises and stores the CUDA-event duration of the
- * dominant kernel (bucket accumulation) of the LAST chunk. */
+/* Device-resident variant: d_scalars is a CUDA device pointer to nmsm*n*8 uint32 (canonical), d_out64
+ * a device pointer to nmsm*16 uint32 (canonical affine).  Work is enqueued on `cuda_stream` (a
+ * cudaStream_t passed as void*) and the call returns without synchronising; results and the engine's
+ * scalar-range flag are valid once the stream has drained.  If `accumulate_ms` is non-NULL the call
+ * DOES synchronise and stores the CUDA-event duration of the dominant kernel (bucket accumulation)
+ * of the last chunk. */
 int mina_b200_msm_srs_device(int curve, uint32_t nmsm, uint32_t n, const void *d_scalars, void *d_out64,
                              void *cuda_stream, float *accumulate_ms);
 /* MSM engine tuning (takes effect at the next init / table rebuild): window bits and running-sum
  * chunk.  Returns 0 on success. */
 int mina_b200_msm_configure(int curve, int window_bits, int precompute, int leaf);
+
+/* ---- verifier stages ------------------------------------------------------------------------------ */
+/* One bit per stage of the reference's check.  A proof is accepted iff every stage of its kind is in
+ * `passed`; `unavailable` lists stages this build cannot run yet (they force a reject). */
+#define MINA_B200_STAGE_LENGTHS (1u << 0)           /* len <= MAX (lib.rs:48-56) */
+#define MINA_B200_STAGE_DECODE_PROOF (1u << 1)      /* bincode (lib.rs:58-64) */
+#define MINA_B200_STAGE_DECODE_PUB (1u << 2)        /* bincode (lib.rs:65-71) */
+#define MINA_B200_STAGE_PUB_STRUCTURE (1u << 3)     /* ledger-hash comparisons + to_fp (lib.rs:163-186,202-209) */
+#define MINA_B200_STAGE_PUB_HASHES (1u << 4)        /* 17 Poseidon state hashes (lib.rs:128-160,188) */
+#define MINA_B200_STAGE_CONSENSUS (1u << 5)         /* select_secure_chain == Candidate (lib.rs:83-94) */
+#define MINA_B200_STAGE_ACCUMULATOR (1u << 6)       /* accumulator_check: Vesta MSM 2^16 (verify_block) */
+#define MINA_B200_STAGE_STEP_ACCUMULATORS (1u << 7) /* the wrap proof's two previous-challenge accumulators (Pallas 2^15) */
+#define MINA_B200_STAGE_KIMCHI (1u << 8)            /* kimchi to_batch + IPA final check (verify_block) */
+#define MINA_B200_STAGE_ACCOUNT_ABI (1u << 9)       /* Solidity ABI re-encode + compare (mina_account lib.rs:54-66) */
+#define MINA_B200_STAGE_ACCOUNT_LEAF (1u << 10)     /* Account::hash (mina_account lib.rs:70) */
+#define MINA_B200_STAGE_MERKLE (1u << 11)           /* verify_merkle_proof (merkle_verifier.rs:9-35) */
+#define MINA_B200_STAGE_INTERNAL_ERROR (1u << 31)   /* device / allocation failure: rejected */
+typedef struct {
+    uint32_t passed, failed, unavailable;
+} mina_b200_stage_report;
+
+#define MINA_B200_MODE_PER_PROOF 0 /* one MSM per accumulator, like the reference */
+#define MINA_B200_MODE_RLC 1       /* random linear combination over the batch + bisection (default) */
+
+/* Stage report of the last verify_mina_state_ffi / verify_account_inclusion_ffi call on this thread. */
+void mina_b200_last_stages(mina_b200_stage_report *out);
+/* The batch verifier with per-proof reports.  reports / accept_out may be NULL. */
+int mina_b200_verify_state_stages(size_t n, const unsigned char *const *proofs, const size_t *proof_lens,
+                                  const unsigned char *const *pub_inputs, const size_t *pub_input_lens, int mode,
+                                  mina_b200_stage_report *reports, uint8_t *accept_out);
+int mina_b200_verify_account_stages(size_t n, const unsigned char *const *proofs, const size_t *proof_lens,
+                                    const unsigned char *const *pub_inputs, const size_t *pub_input_lens,
+                                    mina_b200_stage_report *reports, uint8_t *accept_out);
+/* accumulator_check from raw proof bytes: ok3 = {wrap/Vesta, step/Pallas #0, #1}. */
+int mina_b200_accumulator_check(const unsigned char *proof, size_t proof_len, uint8_t ok3[3]);
+int mina_b200_accumulator_check_batch(size_t n, const unsigned char *const *proofs, const size_t *proof_lens, int mode, uint8_t *ok3);
+
+/* ---- K4 / K2 / K5: IPA scalar helpers (host buffers, canonical 32-byte field elements) -------------- */
+/* ScalarChallenge::to_field for n 16-byte prechallenges landing in `field` (endo = that field's endo_r). */
+int mina_b200_endo_to_field(int field, uint32_t n, const uint8_t *pre16, uint8_t *out32);
+/* b_poly_coefficients for nproofs x k challenges (8 <= k <= 16): out is nproofs * 2^k elements. */
+int mina_b200_bpoly_coeffs(int field, uint32_t nproofs, int k, const uint8_t *chals32, uint8_t *out32);
+/* sum_j r_j * b_poly_coefficients(chals_j): out is 2^k elements. */
+int mina_b200_bpoly_combine(int field, uint32_t nproofs, int k, const uint8_t *chals32, const uint8_t *r32, uint8_t *out32);
+/* b_poly(chals_j, x_{j,t}) for npts points per proof. */
+int mina_b200_bpoly_eval(int field, uint32_t nproofs, uint32_t npts, int k, const uint8_t *chals32, const uint8_t *x32, uint8_t *out32);
+
+/* ---- K3: Poseidon (table-driven; see csrc/poseidon.hpp for the parity status of the constants) ------- */
+/* table = 174 x 32 bytes (MDS row-major, then 55 x 3 round constants).  states: n x 96 bytes, in place. */
+int mina_b200_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96);
+/* Merkle fold (merkle_verifier.rs:9-35) of nproofs paths of up to max_depth nodes: tags[p*max_depth+d]
+ * (0 = Left, 1 = Right), siblings32 likewise, Fp only.  ok[p] = folded root == roots32[p]. */
+int mina_b200_merkle_fold(const uint8_t *table, uint32_t nproofs, uint32_t max_depth, const uint32_t *depths, const uint8_t *tags,
+                          const uint8_t *siblings32, const uint8_t *leaves32, const uint8_t *roots32, uint8_t *ok, uint8_t *folded32);
+/* 1 iff a table from <data_dir>/poseidon_fp_kimchi.bin passed the reference's known-answer test. */
+int mina_b200_poseidon_trusted(void);
 
 /* ---- field self-test hook (parity tests of the device arithmetic) ------------------------------- */
 /* op: 0 mul, 1 add, 2 sub, 3 inverse (b ignored), 4 square (b ignored).  n elements each. */
@@ -83,6 +144,33 @@ int mina_b200_host_srs_derive(int curve, uint32_t first, uint32_t count, uint8_t
 /* Derive both SRS on the host and store them under cache_dir (what mina_b200_init loads). */
 int mina_b200_host_build_srs_cache(const char *cache_dir);
 int mina_b200_host_blake2b512(const uint8_t *data, size_t len, uint8_t out[64]);
+
+/* Wire decoders (csrc/wire.hpp).  kind: 0 state proof, 1 state pub, 2 account proof, 3 account pub.
+ * Returns 0 and fills `summary` (see the field list in csrc/abi_host.cu), or -1 on a decode error. */
+typedef struct {
+    uint64_t consumed;       /* bytes read */
+    uint64_t proof_end;      /* state proof: end of the Pickles proof (13 849 in the fixture) */
+    uint32_t n_step_comms, n_lr, merkle_depth, is_devnet;
+    uint32_t blockchain_length[17], curr_global_slot[17], epoch_count[17], min_window_density[17];
+    uint64_t state_begin[17], state_end[17];
+    uint8_t previous_state_hash[17][32], first_pass_ledger[17][32];
+    uint8_t wrap_sg[64], step_sg[2][64];
+    uint8_t hash0[32];       /* state pub: bridge tip hash; account pub: ledger hash */
+    uint64_t encoded_account_len, balance;
+    uint32_t nonce, has_zkapp;
+} mina_b200_wire_summary;
+int mina_b200_host_decode(int kind, const uint8_t *data, size_t len, mina_b200_wire_summary *summary);
+/* select_secure_chain (consensus_state.rs:22-37) on two bincode-encoded protocol states.
+ * *result: 0 = Bridge, 1 = Candidate.  Returns 0, -1 decode error, -2 constants differ (the reference's
+ * Err), -3 the tie needs Poseidon state hashes. */
+int mina_b200_host_select_secure_chain(const uint8_t *candidate, size_t candidate_len, const uint8_t *tip, size_t tip_len, int *result);
+/* Verification-key loader (verifier_index.rs:109-276).  out32: 28 x 64 bytes of commitments (canonical),
+ * then shifts[7], group_gen, zk_w3, zkpm[4], endo as 32-byte canonical Fq = 28*64 + 14*32 bytes;
+ * meta: log_size_of_group, max_poly_size, public, prev_challenges.  -1 on error (see last_error). */
+int mina_b200_host_vk_load(const char *path, uint8_t *out, uint32_t meta[4]);
+/* Host Poseidon sponge: hash_with_kimchi(prefix, xs[0..n)) with the given table (Fp). */
+int mina_b200_host_hash_with_kimchi(const uint8_t *table, const char *prefix, const uint8_t *xs32, uint32_t n, uint8_t out32[32]);
+int mina_b200_host_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,7 @@
 The package is a thin Python mirror of the C ABI in include/*.h; all arithmetic runs in the native
 library (CUDA kernels for sm_100a + a C++ host driver).  There is no CPU fallback.
 """
+from .ffi import *  # noqa: F401,F403
 from .ffi import (  # noqa: F401
     MinaB200Error,
     field_op,

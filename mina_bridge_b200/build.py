@@ -77,10 +77,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-Xcompiler", "-pthread"])
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl",
+                           "-Xcompiler", "-pthread"])
     for alias in ("libmina_state_verifier_ffi.so", "libmina_account_verifier_ffi.so"):
         # the names the reference's cgo LDFLAGS link (AL/operator/mina/mina.go:3-8,
-        # AL/operator/mina_account/mina_account.go:3-8)
+        # AL/operator/mina_account/mina_account.go:3-8); both entry points live in the one library
         dst = os.path.join(LIBDIR, alias)
         if os.path.lexists(dst):
             os.remove(dst)

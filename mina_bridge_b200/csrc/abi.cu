@@ -1,9 +1,15 @@
-// C ABI: lifecycle, MSM entry points and device self-test hooks (include/mina_b200.h).
+// C ABI: lifecycle, MSM entry points, IPA / Poseidon kernel hooks and device self-test hooks
+// (include/mina_b200.h).  The verifier entry points live in verifier.cu.
+#include <dlfcn.h>
+
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/mina_b200.h"
 #include "context.cuh"
+#include "ipa.cuh"
+#include "poseidon.cuh"
 
 namespace pasta {
 
@@ -17,16 +23,51 @@ Context &ctx() {
 void require_ready() {
     if (!ctx().ready) throw std::runtime_error("mina_b200: not initialised (call mina_b200_init; a CUDA device is required)");
 }
+uint64_t engine_launches() {
+    uint64_t n = 0;
+    Context &c = ctx();
+    for (int k = 0; k < 2; k++) {
+        if (c.curve[k].fixed) n += c.curve[k].fixed->launches();
+        if (c.curve[k].var) n += c.curve[k].var->launches();
+    }
+    return n;
+}
+
+// Persistent scratch of the low-level entry points (grow-only; guarded by Context::mu).
+struct AbiScratch {
+    DevBuf<uint32_t> scalars[2];  // double-buffered H2D staging of scalar chunks
+    DevBuf<affine> out;
+    DevBuf<uint32_t> out_can, pts_can;
+    DevBuf<affine> pts;
+    DevBuf<fe> a, b, c, d;
+    DevBuf<uint8_t> bytes;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    ~AbiScratch() {
+        for (int i = 0; i < 2; i++) {
+            if (copied[i]) cudaEventDestroy(copied[i]);
+            if (consumed[i]) cudaEventDestroy(consumed[i]);
+        }
+    }
+};
+static AbiScratch *g_scratch = nullptr;
+static AbiScratch &scratch() {
+    if (!g_scratch) {
+        g_scratch = new AbiScratch();
+        for (int i = 0; i < 2; i++) {
+            CTX_CUDA_OK(cudaEventCreateWithFlags(&g_scratch->copied[i], cudaEventDisableTiming));
+            CTX_CUDA_OK(cudaEventCreateWithFlags(&g_scratch->consumed[i], cudaEventDisableTiming));
+        }
+    }
+    return *g_scratch;
+}
 
 template <class B>
 static void upload_srs(CurveCtx &cc, const host::Srs<B> &srs, uint32_t depth, cudaStream_t s) {
     cc.depth = depth;
-    std::vector<uint64_t> flat((size_t)(depth + 1) * 8);
+    std::vector<uint64_t> flat = host::srs_payload(srs);
     cc.host_canonical.resize((size_t)(depth + 1) * 64);
     for (uint32_t i = 0; i <= depth; i++) {
         const host::Affine<B> &p = i < depth ? srs.g[i] : srs.h;
-        std::memcpy(&flat[(size_t)i * 8], p.x.l, 32);
-        std::memcpy(&flat[(size_t)i * 8 + 4], p.y.l, 32);
         p.x.to_bytes_le(&cc.host_canonical[(size_t)i * 64]);
         p.y.to_bytes_le(&cc.host_canonical[(size_t)i * 64 + 32]);
     }
@@ -35,17 +76,70 @@ static void upload_srs(CurveCtx &cc, const host::Srs<B> &srs, uint32_t depth, cu
     CTX_CUDA_OK(cudaStreamSynchronize(s));
 }
 
+// Load the SRS from the cache when its payload matches the compiled-in pin; otherwise derive it by
+// hash-to-curve exactly as the reference does at first use (lib.rs:34, verifier_index.rs:204-208),
+// check the derivation against the same pin, and store it for the next process.
 template <class B>
-static host::Srs<B> load_or_create_srs(const char *cache_dir, const char *name, uint32_t depth) {
+static host::Srs<B> load_or_create_srs(const std::string &dir, const char *name, uint32_t depth) {
     host::Srs<B> srs;
     std::string path;
-    if (cache_dir && *cache_dir) {
-        path = std::string(cache_dir) + "/" + name + "_" + std::to_string(depth) + ".srsbin";
+    if (!dir.empty()) {
+        path = dir + "/" + name + "_" + std::to_string(depth) + ".srsbin";
         if (host::srs_load_cache<B>(path, depth, srs)) return srs;
     }
     srs = host::srs_create<B>(depth);
+    if (!host::srs_matches_pin<B>(srs)) throw std::runtime_error(std::string("SRS derivation does not match the pinned digest: ") + name);
     if (!path.empty()) host::srs_store_cache<B>(path, srs);  // best effort
     return srs;
+}
+
+static std::string default_data_dir() {
+    if (const char *e = std::getenv("MINA_B200_DATA_DIR")) return e;
+    Dl_info info;
+    if (dladdr((void *)&default_data_dir, &info) && info.dli_fname) {
+        std::string so = info.dli_fname;
+        size_t slash = so.rfind('/');
+        std::string dir = slash == std::string::npos ? "." : so.substr(0, slash);
+        return dir + "/../data";  // mina_bridge_b200/lib/libmina_b200.so -> mina_bridge_b200/data
+    }
+    return "";
+}
+
+static void load_keys_and_tables(Context &c) {
+    // verification keys: failure is remembered, not fatal -- only state verification needs them
+    try {
+        c.vk[0] = vk::load_verifier_index(c.data_dir + "/mainnet_vk.json");
+        c.vk[1] = vk::load_verifier_index(c.data_dir + "/devnet_vk.json");
+        c.vk_loaded = true;
+    } catch (const std::exception &e) {
+        c.vk_loaded = false;
+        c.vk_error = e.what();
+    }
+    // Poseidon tables: optional data; trusted only when the reference's known-answer test passes
+    bool fp = c.poseidon_fp.from_file(c.data_dir + "/poseidon_fp_kimchi.bin");
+    bool fq = c.poseidon_fq.from_file(c.data_dir + "/poseidon_fq_kimchi.bin");
+    c.poseidon_trusted = fp && poseidon::passes_reference_kat(c.poseidon_fp);
+    if (!c.poseidon_trusted) c.poseidon_fp.loaded = false;
+    if (!fq || !c.poseidon_trusted) c.poseidon_fq.loaded = false;
+}
+
+static void destroy_device_state(Context &c) {
+    verifier_release(c);
+    delete g_scratch;
+    g_scratch = nullptr;
+    for (int k = 0; k < 2; k++) {
+        c.curve[k].fixed.reset();
+        c.curve[k].var.reset();
+        if (c.curve[k].d_srs) cudaFree(c.curve[k].d_srs);
+        c.curve[k].d_srs = nullptr;
+        if (c.d_poseidon_tab[k]) cudaFree(c.d_poseidon_tab[k]);
+        c.d_poseidon_tab[k] = nullptr;
+    }
+    if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    c.stream = c.copy_stream = nullptr;
+    c.ready = false;
+    c.device = -1;
 }
 
 }  // namespace pasta
@@ -67,7 +161,7 @@ using namespace pasta;
 extern "C" {
 
 const char *mina_b200_last_error(void) { return g_last_error.c_str(); }
-uint64_t mina_b200_launch_count(void) { return ctx().launches.load(); }
+uint64_t mina_b200_launch_count(void) { return ctx().launches.load() + engine_launches(); }
 
 int mina_b200_msm_configure(int curve, int window_bits, int precompute, int leaf) {
     ABI_TRY
@@ -78,39 +172,61 @@ int mina_b200_msm_configure(int curve, int window_bits, int precompute, int leaf
     cfg.c = window_bits;
     cfg.precompute = precompute != 0;
     cfg.leaf = leaf;
-    c.curve[curve].cfg = cfg;
     if (c.ready) {
-        c.curve[curve].fixed->set_bases(c.curve[curve].d_srs, c.curve[curve].depth, cfg, c.stream);
+        CTX_CUDA_OK(cudaSetDevice(c.device));
+        c.curve[curve].fixed->set_bases(c.curve[curve].d_srs, c.curve[curve].depth, cfg, c.stream);  // throws before mutating
         CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
     }
+    c.curve[curve].cfg = cfg;
     return 0;
     ABI_CATCH
 }
 
-int mina_b200_init(int device, const char *cache_dir) {
+int mina_b200_init(int device, const char *data_dir) {
     ABI_TRY
     Context &c = ctx();
     std::lock_guard<std::mutex> lk(c.mu);
-    if (c.ready) return 0;
+    if (c.ready) {
+        if (device != c.device) throw std::runtime_error("mina_b200_init: already initialised on device " + std::to_string(c.device));
+        return 0;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         throw std::runtime_error("mina_b200_init: no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) throw std::runtime_error("mina_b200_init: bad device index");
-    CTX_CUDA_OK(cudaSetDevice(device));
-    c.device = device;
-    CTX_CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    // Both files in the reference hold 65536 points; the Pallas side only ever uses the first 2^15.
-    c.srs_vesta = load_or_create_srs<FqParams>(cache_dir, "vesta", VESTA_SRS_DEPTH);
-    c.srs_pallas = load_or_create_srs<FpParams>(cache_dir, "pallas", PALLAS_SRS_DEPTH);
-    upload_srs<FpParams>(c.curve[0], c.srs_pallas, PALLAS_SRS_DEPTH, c.stream);
-    upload_srs<FqParams>(c.curve[1], c.srs_vesta, VESTA_SRS_DEPTH, c.stream);
-    for (int k = 0; k < 2; k++) {
-        c.curve[k].fixed.reset(make_msm_engine(k));
-        c.curve[k].var.reset(make_msm_engine(k));
-        c.curve[k].fixed->set_bases(c.curve[k].d_srs, c.curve[k].depth, c.curve[k].cfg, c.stream);
+    try {
+        CTX_CUDA_OK(cudaSetDevice(device));
+        c.device = device;
+        c.data_dir = (data_dir && *data_dir) ? std::string(data_dir) : default_data_dir();
+        CTX_CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CTX_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        // Both files in the reference hold 65536 points; the Pallas side only ever uses the first 2^15.
+        c.srs_vesta = load_or_create_srs<FqParams>(c.data_dir, "vesta", VESTA_SRS_DEPTH);
+        c.srs_pallas = load_or_create_srs<FpParams>(c.data_dir, "pallas", PALLAS_SRS_DEPTH);
+        upload_srs<FpParams>(c.curve[0], c.srs_pallas, PALLAS_SRS_DEPTH, c.stream);
+        upload_srs<FqParams>(c.curve[1], c.srs_vesta, VESTA_SRS_DEPTH, c.stream);
+        for (int k = 0; k < 2; k++) {
+            c.curve[k].fixed.reset(make_msm_engine(k));
+            c.curve[k].var.reset(make_msm_engine(k));
+            c.curve[k].fixed->set_bases(c.curve[k].d_srs, c.curve[k].depth, c.curve[k].cfg, c.stream);
+        }
+        load_keys_and_tables(c);
+        if (c.poseidon_fp.loaded) {
+            auto t = c.poseidon_fp.device_table();
+            CTX_CUDA_OK(cudaMalloc(&c.d_poseidon_tab[0], t.size() * 8));
+            CTX_CUDA_OK(cudaMemcpy(c.d_poseidon_tab[0], t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+        }
+        if (c.poseidon_fq.loaded) {
+            auto t = c.poseidon_fq.device_table();
+            CTX_CUDA_OK(cudaMalloc(&c.d_poseidon_tab[1], t.size() * 8));
+            CTX_CUDA_OK(cudaMemcpy(c.d_poseidon_tab[1], t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+        }
+        CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    } catch (...) {
+        destroy_device_state(c);
+        throw;
     }
-    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
     c.ready = true;
     return 0;
     ABI_CATCH
@@ -121,15 +237,8 @@ void mina_b200_shutdown(void) {
     std::lock_guard<std::mutex> lk(c.mu);
     if (!c.ready) return;
     cudaSetDevice(c.device);
-    for (int k = 0; k < 2; k++) {
-        c.curve[k].fixed.reset();
-        c.curve[k].var.reset();
-        if (c.curve[k].d_srs) cudaFree(c.curve[k].d_srs);
-        c.curve[k].d_srs = nullptr;
-    }
-    cudaStreamDestroy(c.stream);
-    c.stream = nullptr;
-    c.ready = false;
+    cudaDeviceSynchronize();
+    destroy_device_state(c);
 }
 
 int mina_b200_srs_points(int curve, uint32_t first, uint32_t count, uint8_t *out64, uint8_t *h64) {
@@ -144,6 +253,10 @@ int mina_b200_srs_points(int curve, uint32_t first, uint32_t count, uint8_t *out
     ABI_CATCH
 }
 
+static void throw_on_engine_error(MsmEngineBase &e, cudaStream_t s) {
+    if (e.take_error(s) & 1u) throw std::runtime_error("msm: a scalar is >= 2^255 (not a canonical field element); result discarded");
+}
+
 int mina_b200_msm_srs_device(int curve, uint32_t nmsm, uint32_t n, const void *d_scalars, void *d_out64,
                              void *cuda_stream, float *accumulate_ms) {
     ABI_TRY
@@ -154,16 +267,15 @@ int mina_b200_msm_srs_device(int curve, uint32_t nmsm, uint32_t n, const void *d
     CTX_CUDA_OK(cudaSetDevice(c.device));
     CurveCtx &cc = c.curve[curve];
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    DevBuf<affine> out(nmsm);
+    AbiScratch &sc = scratch();
+    affine *out = sc.out.reserve(std::max<uint32_t>(nmsm, 1));
     cc.fixed->enable_kernel_timing(accumulate_ms != nullptr);
-    cc.fixed->run((const uint32_t *)d_scalars, nmsm, n, out.p, s);
-    launch_affine_from_mont(curve, out.p, (uint32_t *)d_out64, nmsm, s);
-    c.launches += (uint64_t)cc.fixed->launches_per_run() + 1;
-    if (accumulate_ms) {
+    cc.fixed->run((const uint32_t *)d_scalars, nmsm, n, out, s);
+    launch_affine_from_mont(curve, out, (uint32_t *)d_out64, nmsm, s);
+    c.launches += 1;
+    if (accumulate_ms) {  // the only case that synchronises
         CTX_CUDA_OK(cudaStreamSynchronize(s));
         *accumulate_ms = cc.fixed->last_accumulate_ms();
-    } else {
-        CTX_CUDA_OK(cudaStreamSynchronize(s));  // `out` is freed on return
     }
     return 0;
     ABI_CATCH
@@ -179,17 +291,29 @@ int mina_b200_msm_srs(int curve, uint32_t nmsm, uint32_t n, const uint8_t *scala
     CurveCtx &cc = c.curve[curve];
     if (n > cc.depth) throw std::runtime_error("msm_srs: n exceeds the resident SRS depth");
     if (nmsm == 0) return 0;
-    size_t nsc = (size_t)nmsm * n;
-    DevBuf<uint32_t> d_sc(std::max<size_t>(nsc * 8, 8));
-    DevBuf<affine> d_out(nmsm);
-    DevBuf<uint32_t> d_can((size_t)nmsm * 16);
-    if (nsc) CTX_CUDA_OK(cudaMemcpyAsync(d_sc.p, scalars32, nsc * 32, cudaMemcpyHostToDevice, c.stream));
+    AbiScratch &sc = scratch();
+    affine *out = sc.out.reserve(nmsm);
+    uint32_t *can = sc.out_can.reserve((size_t)nmsm * 16);
     cc.fixed->enable_kernel_timing(false);
-    cc.fixed->run(d_sc.p, nmsm, n, d_out.p, c.stream);
-    launch_affine_from_mont(curve, d_out.p, d_can.p, nmsm, c.stream);
-    CTX_CUDA_OK(cudaMemcpyAsync(out64, d_can.p, (size_t)nmsm * 64, cudaMemcpyDeviceToHost, c.stream));
-    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
-    c.launches += (uint64_t)cc.fixed->launches_per_run() + 1;
+    // Chunked, double-buffered: the H2D copy of chunk k+1 (copy stream) overlaps the MSMs of chunk k.
+    const size_t per = (size_t)n * 8;
+    uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(nmsm, (16u << 20) / std::max<size_t>(per * 4, 1)));
+    for (int b = 0; b < 2; b++) sc.scalars[b].reserve(std::max<size_t>((size_t)chunk * per, 8));
+    uint32_t idx = 0;
+    for (uint32_t done = 0; done < nmsm; done += chunk, idx++) {
+        uint32_t cur = std::min(chunk, nmsm - done);
+        int b = idx & 1;
+        if (idx >= 2) CTX_CUDA_OK(cudaStreamWaitEvent(c.copy_stream, sc.consumed[b], 0));
+        if (per) CTX_CUDA_OK(cudaMemcpyAsync(sc.scalars[b].p, scalars32 + (size_t)done * per * 4, (size_t)cur * per * 4, cudaMemcpyHostToDevice, c.copy_stream));
+        CTX_CUDA_OK(cudaEventRecord(sc.copied[b], c.copy_stream));
+        CTX_CUDA_OK(cudaStreamWaitEvent(c.stream, sc.copied[b], 0));
+        cc.fixed->run(sc.scalars[b].p, cur, n, out + done, c.stream);
+        CTX_CUDA_OK(cudaEventRecord(sc.consumed[b], c.stream));
+    }
+    launch_affine_from_mont(curve, out, can, nmsm, c.stream);
+    c.launches += 1;
+    CTX_CUDA_OK(cudaMemcpyAsync(out64, can, (size_t)nmsm * 64, cudaMemcpyDeviceToHost, c.stream));
+    throw_on_engine_error(*cc.fixed, c.stream);  // synchronises
     return 0;
     ABI_CATCH
 }
@@ -207,11 +331,17 @@ int mina_b200_msm(int curve, uint32_t n, const uint8_t *scalars32, const uint8_t
         std::memset(out64, 0, 64);
         return 0;
     }
-    DevBuf<uint32_t> d_sc((size_t)n * 8), d_pts_can((size_t)n * 16), d_can(16);
-    DevBuf<affine> d_pts(n), d_out(1);
-    CTX_CUDA_OK(cudaMemcpyAsync(d_sc.p, scalars32, (size_t)n * 32, cudaMemcpyHostToDevice, c.stream));
-    CTX_CUDA_OK(cudaMemcpyAsync(d_pts_can.p, points64, (size_t)n * 64, cudaMemcpyHostToDevice, c.stream));
-    launch_affine_to_mont(curve, d_pts_can.p, d_pts.p, n, c.stream);
+    AbiScratch &sc = scratch();
+    uint32_t *d_sc = sc.scalars[0].reserve((size_t)n * 8);
+    uint32_t *d_pts_can = sc.pts_can.reserve((size_t)n * 16);
+    affine *d_pts = sc.pts.reserve(n);
+    affine *d_out = sc.out.reserve(1);
+    uint32_t *d_can = sc.out_can.reserve(16);
+    uint8_t *d_bad = sc.bytes.reserve(4);
+    CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, scalars32, (size_t)n * 32, cudaMemcpyHostToDevice, c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_pts_can, points64, (size_t)n * 64, cudaMemcpyHostToDevice, c.stream));
+    launch_affine_to_mont_checked(curve, d_pts_can, d_pts, n, (uint32_t *)d_bad, c.stream);
     MsmConfig cfg;
     cfg.precompute = false;
     if (window_bits > 0)
@@ -222,15 +352,132 @@ int mina_b200_msm(int curve, uint32_t n, const uint8_t *scalars32, const uint8_t
         while ((1u << lg) < n) lg++;
         cfg.c = lg <= 6 ? 4 : (lg - 2 > 16 ? 16 : lg - 2);
     }
-    cc.var->set_bases(d_pts.p, n, cfg, c.stream);
-    cc.var->run(d_sc.p, 1, n, d_out.p, c.stream);
-    launch_affine_from_mont(curve, d_out.p, d_can.p, 1, c.stream);
-    CTX_CUDA_OK(cudaMemcpyAsync(out64, d_can.p, 64, cudaMemcpyDeviceToHost, c.stream));
-    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
-    c.launches += (uint64_t)cc.var->launches_per_run() + 2;
+    cc.var->set_bases(d_pts, n, cfg, c.stream);
+    cc.var->run(d_sc, 1, n, d_out, c.stream);
+    launch_affine_from_mont(curve, d_out, d_can, 1, c.stream);
+    c.launches += 2;
+    CTX_CUDA_OK(cudaMemcpyAsync(out64, d_can, 64, cudaMemcpyDeviceToHost, c.stream));
+    uint32_t bad = 0;
+    CTX_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
+    throw_on_engine_error(*cc.var, c.stream);  // synchronises
+    if (bad) throw std::runtime_error("msm: a base point is non-canonical or not on the curve");
     return 0;
     ABI_CATCH
 }
+
+// ---- K4 / K2 / K5 / K3 hooks: host buffers in, host buffers out, canonical field elements --------------
+int mina_b200_endo_to_field(int field, uint32_t n, const uint8_t *pre16, uint8_t *out32) {
+    ABI_TRY
+    require_ready();
+    if (!n) return 0;
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    AbiScratch &sc = scratch();
+    uint8_t *d_pre = sc.bytes.reserve((size_t)n * 16);
+    fe *d_m = sc.a.reserve(n), *d_o = sc.b.reserve(n);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_pre, pre16, (size_t)n * 16, cudaMemcpyHostToDevice, c.stream));
+    launch_endo_to_field(field, d_pre, d_m, n, c.stream);
+    launch_fe_from_mont(field, d_m, d_o, n, c.stream);
+    c.launches += 2;
+    CTX_CUDA_OK(cudaMemcpyAsync(out32, d_o, (size_t)n * 32, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+    ABI_CATCH
+}
+
+int mina_b200_bpoly_coeffs(int field, uint32_t nproofs, int k, const uint8_t *chals32, uint8_t *out32) {
+    ABI_TRY
+    require_ready();
+    if (!nproofs) return 0;
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    AbiScratch &sc = scratch();
+    size_t nch = (size_t)nproofs * k, total = (size_t)nproofs << k;
+    fe *d_c = sc.a.reserve(nch), *d_cm = sc.b.reserve(nch), *d_t = sc.c.reserve((size_t)nproofs * BPOLY_TABLE), *d_o = sc.d.reserve(total);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_c, chals32, nch * 32, cudaMemcpyHostToDevice, c.stream));
+    launch_fe_to_mont(field, d_c, d_cm, (uint32_t)nch, c.stream);
+    launch_bpoly_tables(field, d_cm, d_t, nproofs, k, nullptr, true, c.stream);
+    launch_bpoly_materialize(field, d_t, d_o, nproofs, k, c.stream);
+    c.launches += 3;
+    CTX_CUDA_OK(cudaMemcpyAsync(out32, d_o, total * 32, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+    ABI_CATCH
+}
+
+int mina_b200_bpoly_combine(int field, uint32_t nproofs, int k, const uint8_t *chals32, const uint8_t *r32, uint8_t *out32) {
+    ABI_TRY
+    require_ready();
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    AbiScratch &sc = scratch();
+    size_t nch = (size_t)nproofs * k, total = (size_t)1 << k;
+    fe *d_in = sc.a.reserve(nch + nproofs + 1), *d_m = sc.b.reserve(nch + nproofs + 1);
+    fe *d_t = sc.c.reserve((size_t)std::max<uint32_t>(nproofs, 1) * BPOLY_TABLE), *d_o = sc.d.reserve(total);
+    if (nproofs) {
+        CTX_CUDA_OK(cudaMemcpyAsync(d_in, chals32, nch * 32, cudaMemcpyHostToDevice, c.stream));
+        CTX_CUDA_OK(cudaMemcpyAsync(d_in + nch, r32, (size_t)nproofs * 32, cudaMemcpyHostToDevice, c.stream));
+        launch_fe_to_mont(field, d_in, d_m, (uint32_t)(nch + nproofs), c.stream);
+        launch_bpoly_tables(field, d_m, d_t, nproofs, k, d_m + nch, false, c.stream);
+    }
+    launch_bpoly_combine(field, d_t, nullptr, nproofs, k, d_o, c.stream);
+    c.launches += 3;
+    CTX_CUDA_OK(cudaMemcpyAsync(out32, d_o, total * 32, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+    ABI_CATCH
+}
+
+int mina_b200_bpoly_eval(int field, uint32_t nproofs, uint32_t npts, int k, const uint8_t *chals32, const uint8_t *x32, uint8_t *out32) {
+    ABI_TRY
+    require_ready();
+    size_t nch = (size_t)nproofs * k, nx = (size_t)nproofs * npts;
+    if (!nx) return 0;
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    AbiScratch &sc = scratch();
+    fe *d_in = sc.a.reserve(nch + nx), *d_m = sc.b.reserve(nch + nx), *d_o = sc.c.reserve(nx), *d_oc = sc.d.reserve(nx);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_in, chals32, nch * 32, cudaMemcpyHostToDevice, c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_in + nch, x32, nx * 32, cudaMemcpyHostToDevice, c.stream));
+    launch_fe_to_mont(field, d_in, d_m, (uint32_t)(nch + nx), c.stream);
+    launch_bpoly_eval(field, d_m, d_m + nch, d_o, nproofs, npts, k, c.stream);
+    launch_fe_from_mont(field, d_o, d_oc, (uint32_t)nx, c.stream);
+    c.launches += 3;
+    CTX_CUDA_OK(cudaMemcpyAsync(out32, d_oc, nx * 32, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+    ABI_CATCH
+}
+
+static void table_to_device(int field, const uint8_t *table, fe *d_raw, fe *d_mont, cudaStream_t s) {
+    CTX_CUDA_OK(cudaMemcpyAsync(d_raw, table, (size_t)POSEIDON_TABLE_WORDS * 32, cudaMemcpyHostToDevice, s));
+    launch_fe_to_mont(field, d_raw, d_mont, POSEIDON_TABLE_WORDS, s);
+}
+
+int mina_b200_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96) {
+    ABI_TRY
+    require_ready();
+    if (!n) return 0;
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    AbiScratch &sc = scratch();
+    fe *d_raw = sc.a.reserve(POSEIDON_TABLE_WORDS), *d_tab = sc.b.reserve(POSEIDON_TABLE_WORDS), *d_st = sc.c.reserve((size_t)n * 3);
+    table_to_device(field, table, d_raw, d_tab, c.stream);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_st, states96, (size_t)n * 96, cudaMemcpyHostToDevice, c.stream));
+    launch_poseidon_permute(field, d_tab, d_st, n, c.stream);
+    c.launches += 2;
+    CTX_CUDA_OK(cudaMemcpyAsync(states96, d_st, (size_t)n * 96, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+    ABI_CATCH
+}
+
+int mina_b200_poseidon_trusted(void) { return ctx().ready && ctx().poseidon_trusted ? 1 : 0; }
 
 }  // extern "C"
 

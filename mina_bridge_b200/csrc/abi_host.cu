@@ -4,7 +4,9 @@
 #include <stdexcept>
 
 #include "../../include/mina_b200.h"
+#include "consensus.hpp"
 #include "context.cuh"
+#include "wire.hpp"
 
 using namespace pasta;
 
@@ -50,6 +52,20 @@ void host_srs_t(uint32_t first, uint32_t count, uint8_t *out64, uint8_t *h64) {
     }
 }
 }  // namespace
+
+template <class F>
+static int host_permute_t(const uint8_t *table, uint32_t n, uint8_t *states96) {
+    poseidon::Params<F> params;
+    if (!params.from_bytes(table, (size_t)poseidon::TABLE_WORDS * 32)) return -1;
+    for (uint32_t i = 0; i < n; i++) {
+        host::Fe<F> st[3];
+        for (int k = 0; k < 3; k++)
+            if (!host::Fe<F>::from_bytes_le(states96 + 96 * (size_t)i + 32 * k, st[k])) return -2;
+        poseidon::permute<F>(params, st);
+        for (int k = 0; k < 3; k++) st[k].to_bytes_le(states96 + 96 * (size_t)i + 32 * k);
+    }
+    return 0;
+}
 
 extern "C" {
 
@@ -99,6 +115,158 @@ int mina_b200_host_blake2b512(const uint8_t *data, size_t len, uint8_t out[64]) 
     auto dg = host::Blake2b512::hash(data, len);
     std::memcpy(out, dg.data(), 64);
     return 0;
+}
+
+
+int mina_b200_host_decode(int kind, const uint8_t *data, size_t len, mina_b200_wire_summary *out) {
+    try {
+        std::memset(out, 0, sizeof *out);
+        std::string err;
+        if (kind == 0) {
+            auto p = std::make_unique<wire::StateProof>();
+            if (!wire::decode_state_proof(data, len, *p, err)) {
+                set_error(err);
+                return -1;
+            }
+            const wire::PicklesProof &pp = p->candidate_tip_proof;
+            out->proof_end = pp.wire_end;
+            out->consumed = p->bridge_tip_state.wire_end;
+            out->n_step_comms = (uint32_t)pp.step_challenge_polynomial_commitments.size();
+            out->n_lr = (uint32_t)pp.proof.lr.size();
+            std::memcpy(out->wrap_sg, pp.wrap_challenge_polynomial_commitment.x.data(), 32);
+            std::memcpy(out->wrap_sg + 32, pp.wrap_challenge_polynomial_commitment.y.data(), 32);
+            for (size_t k = 0; k < 2 && k < pp.step_challenge_polynomial_commitments.size(); k++) {
+                std::memcpy(out->step_sg[k], pp.step_challenge_polynomial_commitments[k].x.data(), 32);
+                std::memcpy(out->step_sg[k] + 32, pp.step_challenge_polynomial_commitments[k].y.data(), 32);
+            }
+            for (int i = 0; i < 17; i++) {
+                const wire::ProtocolState &st = i < 16 ? p->candidate_chain_states[i] : p->bridge_tip_state;
+                out->blockchain_length[i] = st.consensus_state.blockchain_length;
+                out->curr_global_slot[i] = st.consensus_state.curr_global_slot;
+                out->epoch_count[i] = st.consensus_state.epoch_count;
+                out->min_window_density[i] = st.consensus_state.min_window_density;
+                out->state_begin[i] = st.wire_begin;
+                out->state_end[i] = st.wire_end;
+                std::memcpy(out->previous_state_hash[i], st.previous_state_hash.data(), 32);
+                std::memcpy(out->first_pass_ledger[i], st.blockchain_state.target.first_pass_ledger.data(), 32);
+            }
+            return 0;
+        }
+        if (kind == 1) {
+            wire::StatePubInputs pub;
+            if (!wire::decode_state_pub(data, len, pub, err)) {
+                set_error(err);
+                return -1;
+            }
+            out->consumed = 1 + 33 * 32;
+            out->is_devnet = pub.is_state_proof_from_devnet;
+            std::memcpy(out->hash0, pub.bridge_tip_state_hash.data(), 32);
+            for (int i = 0; i < 16; i++) {
+                std::memcpy(out->previous_state_hash[i], pub.candidate_chain_state_hashes[i].data(), 32);
+                std::memcpy(out->first_pass_ledger[i], pub.candidate_chain_ledger_hashes[i].data(), 32);
+            }
+            return 0;
+        }
+        if (kind == 2) {
+            wire::AccountProof ap;
+            wire::Reader probe(data, len);
+            if (!wire::decode_account_proof(data, len, ap, err)) {
+                set_error(err);
+                return -1;
+            }
+            out->merkle_depth = (uint32_t)ap.merkle_path.size();
+            out->balance = ap.account.balance;
+            out->nonce = ap.account.nonce;
+            out->has_zkapp = ap.account.has_zkapp;
+            std::memcpy(out->hash0, ap.account.public_key.x.data(), 32);
+            return 0;
+        }
+        if (kind == 3) {
+            wire::AccountPubInputs pub;
+            if (!wire::decode_account_pub(data, len, pub, err)) {
+                set_error(err);
+                return -1;
+            }
+            out->consumed = 40 + pub.encoded_account.size();
+            out->encoded_account_len = pub.encoded_account.size();
+            std::memcpy(out->hash0, pub.ledger_hash.data(), 32);
+            return 0;
+        }
+        set_error("bad kind");
+        return -1;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return -1;
+    }
+}
+
+int mina_b200_host_select_secure_chain(const uint8_t *candidate, size_t candidate_len, const uint8_t *tip, size_t tip_len, int *result) {
+    try {
+        wire::ProtocolState c, t;
+        wire::Reader rc(candidate, candidate_len), rt(tip, tip_len);
+        wire::read_protocol_state(rc, c);
+        wire::read_protocol_state(rt, t);
+        if (!rc.ok() || !rt.ok()) {
+            set_error(rc.ok() ? rt.error() : rc.error());
+            return -1;
+        }
+        consensus::ChainResult res = consensus::ChainResult::Bridge;
+        consensus::Status st = consensus::select_secure_chain(c, t, consensus::StateHashCmp(), res);
+        if (st == consensus::Status::ConstantsDiffer) return -2;
+        if (st == consensus::Status::NeedStateHash) return -3;
+        *result = res == consensus::ChainResult::Candidate ? 1 : 0;
+        return 0;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return -1;
+    }
+}
+
+int mina_b200_host_vk_load(const char *path, uint8_t *out, uint32_t meta[4]) {
+    try {
+        vk::VerifierIndex vi = vk::load_verifier_index(path);
+        auto comms = vi.all_commitments();
+        uint8_t *o = out;
+        for (auto &p : comms) {
+            if (!p.on_curve()) throw std::runtime_error("vk: commitment is not on Pallas");
+            p.x.to_bytes_le(o);
+            p.y.to_bytes_le(o + 32);
+            o += 64;
+        }
+        for (int i = 0; i < 7; i++, o += 32) vi.shift[i].to_bytes_le(o);
+        vi.group_gen.to_bytes_le(o);
+        o += 32;
+        vi.w.to_bytes_le(o);
+        o += 32;
+        for (int i = 0; i < 4; i++, o += 32) vi.zkpm[i].to_bytes_le(o);
+        vi.endo.to_bytes_le(o);
+        meta[0] = vi.log_size_of_group;
+        meta[1] = vi.max_poly_size;
+        meta[2] = vi.public_inputs;
+        meta[3] = vi.prev_challenges;
+        return 0;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return -1;
+    }
+}
+
+int mina_b200_host_hash_with_kimchi(const uint8_t *table, const char *prefix, const uint8_t *xs32, uint32_t n, uint8_t out32[32]) {
+    poseidon::Params<FpParams> params;
+    if (!params.from_bytes(table, (size_t)poseidon::TABLE_WORDS * 32)) return -1;
+    std::vector<host::Fp> xs(n);
+    for (uint32_t i = 0; i < n; i++)
+        if (!host::Fp::from_bytes_le(xs32 + 32 * (size_t)i, xs[i])) return -2;
+    host::Fp out;
+    if (!poseidon::hash_with_kimchi<FpParams>(params, prefix, xs.data(), n, out)) return -3;
+    out.to_bytes_le(out32);
+    return 0;
+}
+
+int mina_b200_host_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96) {
+    if (field == 0) return host_permute_t<FpParams>(table, n, states96);
+    if (field == 1) return host_permute_t<FqParams>(table, n, states96);
+    return -1;
 }
 
 }  // extern "C"

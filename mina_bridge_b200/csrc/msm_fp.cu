@@ -9,4 +9,7 @@ void launch_affine_to_mont_fp(const uint32_t *d_in, affine *d_out, uint32_t n, c
 void launch_affine_from_mont_fp(const affine *d_in, uint32_t *d_out, uint32_t n, cudaStream_t s) {
     launch_affine_from_mont_t<FpParams>(d_in, d_out, n, s);
 }
+void launch_affine_to_mont_checked_fp(const uint32_t *d_in, affine *d_out, uint32_t n, uint32_t *d_bad, cudaStream_t s) {
+    launch_affine_to_mont_checked_t<FpParams>(d_in, d_out, n, d_bad, s);
+}
 }  // namespace pasta

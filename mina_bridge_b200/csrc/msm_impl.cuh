@@ -24,9 +24,22 @@
 #include <vector>
 
 #pragma once
+#include "ipa.cuh"
 #include "msm.cuh"
 
 namespace pasta {
+
+// The scalar field of the curve whose coordinates live in F (Pallas: Fp -> Fq, Vesta: Fq -> Fp).
+template <class F>
+struct ScalarFieldOf;
+template <>
+struct ScalarFieldOf<FpParams> {
+    using type = FqParams;
+};
+template <>
+struct ScalarFieldOf<FqParams> {
+    using type = FpParams;
+};
 
 #define CUDA_OK(expr)                                                                              \
     do {                                                                                           \
@@ -46,7 +59,12 @@ struct DigitParams {
     int W;             // windows per scalar
     int wsep;          // 1: one bucket set per window (generic bases); 0: shared (precomputed table)
     uint32_t nbw;      // buckets per window = 2^(c-1)
+    int bpoly_k;       // SRC_BPOLY: log2 of the coefficients per proof (n_used == 1 << bpoly_k)
+    uint32_t *err;     // device flag: bit 0 = a scalar did not fit the signed-digit windows (>= 2^255)
 };
+
+// Where a digit kernel takes its scalars from.
+enum { SRC_MEMORY = 0, SRC_BPOLY = 1 };
 
 // bits [pos, pos+c) of a 256-bit little-endian integer (c <= 24)
 __device__ __forceinline__ uint32_t window_bits(const uint32_t s[8], int pos, int c) {
@@ -57,8 +75,10 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t s[8], int pos, in
     return (uint32_t)(v >> sh) & ((1u << c) - 1u);
 }
 
-// Pass 1 (count) and pass 3 (scatter) walk the digits the same way.
-template <bool SCATTER>
+// Pass 1 (count) and pass 3 (scatter) walk the digits the same way.  With SRC_BPOLY the scalar is
+// b_poly_coefficients(chals_m)[i], rebuilt from the proof's two product tables (one field
+// multiplication, ipa.cuh) instead of being read from a materialised 2 MiB vector.
+template <bool SCATTER, int SRC, class S>
 static __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, DigitParams p,
                                                 uint32_t *__restrict__ counters, uint32_t *__restrict__ pairs) {
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,10 +87,16 @@ static __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restric
     uint32_t m = (uint32_t)(idx / p.n_used);
     uint32_t i = (uint32_t)(idx % p.n_used);
     uint32_t s[8];
-    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + idx * 8);
-    uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
-    s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    if (SRC == SRC_BPOLY) {
+        fe v = bpoly_coeff<S>(reinterpret_cast<const fe *>(scalars) + (size_t)m * BPOLY_TABLE, i);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = v.v[k];
+    } else {
+        const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + idx * 8);
+        uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+        s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    }
     const uint32_t half = 1u << (p.c - 1);
     uint32_t carry = 0;
     uint32_t group_base = m * (p.wsep ? (uint32_t)p.W : 1u);
@@ -89,6 +115,8 @@ static __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restric
             pairs[pos] = entry | (neg << 31);
         }
     }
+    // a carry out of the top window means the scalar needs more than W*c signed-digit bits
+    if (!SCATTER && carry) atomicOr(p.err, 1u);
 }
 
 // ---- exclusive scan over u32 (three small kernels; inputs are a few 10^4 .. 10^7 counters) --------
@@ -346,6 +374,51 @@ __global__ void __launch_bounds__(256) k_affine_to_mont(const uint32_t *__restri
     q.y = Fd<F>::to_mont(y);
     out[i] = q;
 }
+// Same, for untrusted input: flags (bad |= 1) any point whose coordinates are not canonical (>= p)
+// or that is neither (0,0) nor on y^2 = x^3 + 5 -- arkworks' `of_coordinates` does not check, but a
+// verifier fed attacker-chosen points must never run the group law on an off-curve point.
+template <class F>
+__device__ __forceinline__ bool fe_is_canonical(const fe &a) {
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t t = (uint64_t)a.v[i] - F::MOD(i) - borrow;
+        borrow = (uint32_t)(t >> 63);
+    }
+    return borrow != 0;  // a < p
+}
+template <class F>
+__global__ void __launch_bounds__(256) k_affine_to_mont_checked(const uint32_t *__restrict__ in, affine *__restrict__ out, uint32_t n,
+                                                                uint32_t *__restrict__ bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x, y;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        x.v[k] = in[(size_t)i * 16 + k];
+        y.v[k] = in[(size_t)i * 16 + 8 + k];
+    }
+    bool ok = fe_is_canonical<F>(x) && fe_is_canonical<F>(y);
+    affine q;
+    q.x = Fd<F>::to_mont(x);
+    q.y = Fd<F>::to_mont(y);
+    if (ok && !(fe_is_zero(x) && fe_is_zero(y))) {
+        fe rhs = Fd<F>::add(Fd<F>::mul(Fd<F>::sqr(q.x), q.x), Fd<F>::five());
+        ok = fe_eq(Fd<F>::sqr(q.y), rhs);
+    }
+    if (!ok) {
+        atomicOr(bad, 1u);
+        q.x = fe_zero();
+        q.y = fe_zero();
+    }
+    out[i] = q;
+}
+template <class F>
+void launch_affine_to_mont_checked_t(const uint32_t *d_in, affine *d_out, uint32_t n, uint32_t *d_bad, cudaStream_t s) {
+    if (n == 0) return;
+    k_affine_to_mont_checked<F><<<(n + 255) / 256, 256, 0, s>>>(d_in, d_out, n, d_bad);
+}
+
 template <class F>
 __global__ void __launch_bounds__(256) k_affine_from_mont(const affine *__restrict__ in, uint32_t *__restrict__ out, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,71 +446,78 @@ void launch_affine_from_mont_t(const affine *d_in, uint32_t *d_out, uint32_t n, 
 // ---------------------------------------------------------------------------------------------------
 template <class F>
 class MsmEngine : public MsmEngineBase {
+    using S = typename ScalarFieldOf<F>::type;
+
    public:
     ~MsmEngine() override { release(); }
 
     void set_bases(const affine *d_bases, uint32_t n, const MsmConfig &cfg, cudaStream_t s) override {
+        // validate and plan into locals first; members change only once nothing can throw any more
         if (cfg.c < 2 || cfg.c > 20) throw std::runtime_error("msm: window bits out of range");
         if (cfg.leaf < 2 || (cfg.leaf & (cfg.leaf - 1))) throw std::runtime_error("msm: leaf must be a power of two");
-        free_dev(table_own_);
-        cfg_ = cfg;
-        n_bases_ = n;
-        W_ = 255 / cfg.c + 1;
-        nbw_ = 1u << (cfg.c - 1);
-        if (cfg.precompute) {
-            if ((uint64_t)W_ * n >= (1ull << 31)) throw std::runtime_error("msm: table too large for 31-bit entries");
-            CUDA_OK(cudaMalloc(&table_own_, (size_t)W_ * n * sizeof(affine)));
-            CUDA_OK(cudaMemcpyAsync(table_own_, d_bases, (size_t)n * sizeof(affine), cudaMemcpyDeviceToDevice, s));
-            for (int w = 1; w < W_; w++)
-                k_table_next<F><<<(n + 127) / 128, 128, 0, s>>>(table_own_ + (size_t)(w - 1) * n, table_own_ + (size_t)w * n, n, cfg.c);
-            CUDA_OK(cudaGetLastError());
-            table_ = table_own_;
-        } else {
-            if (n >= (1u << 31)) throw std::runtime_error("msm: too many bases");
-            table_ = d_bases;
-        }
-        // reduction plan
-        levels_ = 0;
-        uint32_t N = nbw_;
-        while (N > 1) {
+        const int W = 255 / cfg.c + 1;
+        const uint32_t nbw = 1u << (cfg.c - 1);
+        int levels = 0, log_m[MAX_LEVELS] = {0};
+        for (uint32_t N = nbw; N > 1;) {
             int m = cfg.leaf;
             while ((uint32_t)m > N) m >>= 1;
             int lg = 0;
             while ((1 << lg) < m) lg++;
-            if (levels_ >= MAX_LEVELS) throw std::runtime_error("msm: too many reduction levels");
-            log_m_[levels_++] = lg;
+            if (levels >= MAX_LEVELS) throw std::runtime_error("msm: too many reduction levels");
+            log_m[levels++] = lg;
             N /= m;
         }
-        if (levels_ == 0) {  // c == 1: a single bucket
-            log_m_[0] = 0;
-            levels_ = 1;
+        if (levels == 0) levels = 1;  // c == 1: a single bucket
+        affine *table_new = nullptr;
+        if (cfg.precompute) {
+            if ((uint64_t)W * n >= (1ull << 31)) throw std::runtime_error("msm: table too large for 31-bit entries");
+            CUDA_OK(cudaMalloc(&table_new, (size_t)W * n * sizeof(affine)));
+            cudaError_t e = cudaMemcpyAsync(table_new, d_bases, (size_t)n * sizeof(affine), cudaMemcpyDeviceToDevice, s);
+            for (int w = 1; w < W && e == cudaSuccess; w++) {
+                k_table_next<F><<<(n + 127) / 128, 128, 0, s>>>(table_new + (size_t)(w - 1) * n, table_new + (size_t)w * n, n, cfg.c);
+                launches_++;
+                e = cudaGetLastError();
+            }
+            if (e != cudaSuccess) {
+                cudaFree(table_new);
+                throw std::runtime_error(std::string("msm: table build failed: ") + cudaGetErrorString(e));
+            }
+        } else if (n >= (1u << 31)) {
+            throw std::runtime_error("msm: too many bases");
         }
+        // commit
+        bool same_plan = W == W_ && nbw == nbw_ && levels == levels_ && cfg.precompute == cfg_.precompute;
+        for (int l = 0; l < levels && same_plan; l++) same_plan = log_m[l] == log_m_[l];
+        free_dev(table_own_);
+        table_own_ = table_new;
+        table_ = cfg.precompute ? table_new : d_bases;
+        cfg_ = cfg;
+        n_bases_ = n;
+        W_ = W;
+        nbw_ = nbw;
+        levels_ = levels;
+        for (int l = 0; l < MAX_LEVELS; l++) log_m_[l] = log_m[l];
+        if (!same_plan) drop_workspace();  // the reduction plan sizes the level buffers
     }
 
     void run(const uint32_t *d_scalars, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) override {
-        if (!table_) throw std::runtime_error("msm: no bases set");
-        if (n_used > n_bases_) throw std::runtime_error("msm: n_used exceeds resident bases");
-        if (nmsm == 0) return;
-        const uint32_t groups_per_msm = cfg_.precompute ? 1u : (uint32_t)W_;
-        const uint64_t buckets_per_msm = (uint64_t)groups_per_msm * nbw_;
-        const uint64_t pairs_per_msm = (uint64_t)n_used * W_;
-        // chunk the batch so the workspace stays bounded
-        uint64_t chunk = nmsm;
-        const uint64_t max_buckets = 1ull << 23, max_pairs = 1ull << 28;
-        if (chunk * buckets_per_msm > max_buckets) chunk = max_buckets / buckets_per_msm;
-        if (pairs_per_msm && chunk * pairs_per_msm > max_pairs) chunk = max_pairs / pairs_per_msm;
-        if (chunk == 0) chunk = 1;
-        if (chunk * buckets_per_msm >= (1ull << 32) || chunk * pairs_per_msm >= (1ull << 32))
-            throw std::runtime_error("msm: problem too large for 32-bit indices");
-        ensure_workspace((uint32_t)chunk, n_used);
-        for (uint32_t done = 0; done < nmsm; done += (uint32_t)chunk) {
-            uint32_t cur = (uint32_t)std::min<uint64_t>(chunk, nmsm - done);
-            run_chunk(d_scalars + (size_t)done * n_used * 8, cur, n_used, d_out + done, s);
-        }
+        run_src(SRC_MEMORY, d_scalars, 0, nmsm, n_used, d_out, s);
+    }
+    void run_bpoly(const fe *d_tables, uint32_t nmsm, int k, affine *d_out, cudaStream_t s) override {
+        if (k < BPOLY_LO_BITS || k > 2 * BPOLY_LO_BITS) throw std::runtime_error("msm: bpoly rounds must be in [8, 16]");
+        run_src(SRC_BPOLY, reinterpret_cast<const uint32_t *>(d_tables), k, nmsm, 1u << k, d_out, s);
     }
 
     size_t workspace_bytes() const override { return ws_bytes_ + (table_own_ ? (size_t)W_ * n_bases_ * sizeof(affine) : 0); }
-    int launches_per_run() const override { return 5 + 2 * levels_ + 1; }
+    uint64_t launches() const override { return launches_; }
+    uint32_t take_error(cudaStream_t s) override {
+        if (!err_) return 0;
+        uint32_t h = 0;
+        CUDA_OK(cudaMemcpyAsync(&h, err_, sizeof h, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        if (h) CUDA_OK(cudaMemsetAsync(err_, 0, sizeof h, s));
+        return h;
+    }
     void enable_kernel_timing(bool on) override {
         timing_ = on;
         if (on && !ev0_) {
@@ -459,8 +539,10 @@ class MsmEngine : public MsmEngineBase {
         if (p) cudaFree(p);
         p = nullptr;
     }
-    void release() {
-        free_dev(table_own_);
+    void drop_workspace() {
+        cap_buckets_ = cap_pairs_ = 0;
+        cap_groups_ = 0;
+        ws_bytes_ = 0;
         free_dev(counters_);
         free_dev(offsets_);
         free_dev(tile_sums_);
@@ -470,47 +552,89 @@ class MsmEngine : public MsmEngineBase {
         free_dev(lvlS_[1]);
         free_dev(lvlW_);
         free_dev(sumW_);
+    }
+    void release() {
+        free_dev(table_own_);
+        drop_workspace();
+        free_dev(err_);
         if (ev0_) cudaEventDestroy(ev0_);
         if (ev1_) cudaEventDestroy(ev1_);
         ev0_ = ev1_ = nullptr;
+    }
+
+    void run_src(int src, const uint32_t *d_src, int bpoly_k, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) {
+        if (!table_) throw std::runtime_error("msm: no bases set");
+        if (n_used > n_bases_) throw std::runtime_error("msm: n_used exceeds resident bases");
+        if (nmsm == 0) return;
+        const uint32_t groups_per_msm = cfg_.precompute ? 1u : (uint32_t)W_;
+        const uint64_t buckets_per_msm = (uint64_t)groups_per_msm * nbw_;
+        const uint64_t pairs_per_msm = (uint64_t)n_used * W_;
+        // chunk the batch so the workspace stays bounded
+        uint64_t chunk = nmsm;
+        const uint64_t max_buckets = 1ull << 23, max_pairs = 1ull << 28;
+        if (chunk * buckets_per_msm > max_buckets) chunk = max_buckets / buckets_per_msm;
+        if (pairs_per_msm && chunk * pairs_per_msm > max_pairs) chunk = max_pairs / pairs_per_msm;
+        if (chunk == 0) chunk = 1;
+        if (chunk * buckets_per_msm >= (1ull << 32) || chunk * pairs_per_msm >= (1ull << 32))
+            throw std::runtime_error("msm: problem too large for 32-bit indices");
+        ensure_workspace((uint32_t)chunk, n_used);
+        for (uint32_t done = 0; done < nmsm; done += (uint32_t)chunk) {
+            uint32_t cur = (uint32_t)std::min<uint64_t>(chunk, nmsm - done);
+            const uint32_t *src_ptr = src == SRC_BPOLY ? d_src + (size_t)done * BPOLY_TABLE * 8 : d_src + (size_t)done * n_used * 8;
+            run_chunk(src, src_ptr, bpoly_k, cur, n_used, d_out + done, s);
+        }
     }
 
     void ensure_workspace(uint32_t nmsm, uint32_t n_used) {
         const uint32_t groups = nmsm * (cfg_.precompute ? 1u : (uint32_t)W_);
         const uint64_t nb = (uint64_t)groups * nbw_;
         const uint64_t np = (uint64_t)nmsm * n_used * W_;
+        if (!err_) {
+            CUDA_OK(cudaMalloc(&err_, sizeof(uint32_t)));
+            CUDA_OK(cudaMemset(err_, 0, sizeof(uint32_t)));
+        }
         if (nb <= cap_buckets_ && np <= cap_pairs_ && groups <= cap_groups_) return;
-        free_dev(counters_);
-        free_dev(offsets_);
-        free_dev(tile_sums_);
-        free_dev(pairs_);
-        free_dev(buckets_);
-        free_dev(lvlS_[0]);
-        free_dev(lvlS_[1]);
-        free_dev(lvlW_);
-        free_dev(sumW_);
-        cap_buckets_ = std::max<uint64_t>(nb, cap_buckets_);
-        cap_pairs_ = std::max<uint64_t>(np, cap_pairs_);
-        cap_groups_ = std::max<uint32_t>(groups, cap_groups_);
-        size_t ntiles = (cap_buckets_ + SCAN_TILE - 1) / SCAN_TILE;
-        size_t first = (cap_buckets_ >> log_m_[0]) + 1;
-        ws_bytes_ = 0;
-        auto alloc = [&](auto &ptr, size_t bytes) {
-            CUDA_OK(cudaMalloc(&ptr, bytes));
-            ws_bytes_ += bytes;
+        const uint64_t want_b = std::max<uint64_t>(nb, cap_buckets_), want_p = std::max<uint64_t>(np, cap_pairs_);
+        const uint32_t want_g = std::max<uint32_t>(groups, cap_groups_);
+        drop_workspace();  // caps are zero from here until every allocation below has succeeded
+        size_t ntiles = (want_b + SCAN_TILE - 1) / SCAN_TILE;
+        size_t first = (want_b >> log_m_[0]) + 1;
+        size_t bytes = 0;
+        auto alloc = [&](auto &ptr, size_t b) {
+            cudaError_t e = cudaMalloc(&ptr, b);
+            if (e != cudaSuccess) {
+                drop_workspace();
+                throw std::runtime_error(std::string("msm: workspace allocation failed: ") + cudaGetErrorString(e));
+            }
+            bytes += b;
         };
-        alloc(counters_, (cap_buckets_ + 1) * sizeof(uint32_t));
-        alloc(offsets_, (cap_buckets_ + 1) * sizeof(uint32_t));
+        alloc(counters_, (want_b + 1) * sizeof(uint32_t));
+        alloc(offsets_, (want_b + 1) * sizeof(uint32_t));
         alloc(tile_sums_, (ntiles + 1) * sizeof(uint32_t));
-        alloc(pairs_, std::max<uint64_t>(cap_pairs_, 1) * sizeof(uint32_t));
-        alloc(buckets_, cap_buckets_ * sizeof(xyzz));
+        alloc(pairs_, std::max<uint64_t>(want_p, 1) * sizeof(uint32_t));
+        alloc(buckets_, want_b * sizeof(xyzz));
         alloc(lvlS_[0], first * sizeof(xyzz));
         alloc(lvlS_[1], first * sizeof(xyzz));
         alloc(lvlW_, first * sizeof(xyzz));
-        alloc(sumW_, (size_t)MAX_LEVELS * cap_groups_ * sizeof(xyzz));
+        alloc(sumW_, (size_t)MAX_LEVELS * want_g * sizeof(xyzz));
+        cap_buckets_ = want_b;
+        cap_pairs_ = want_p;
+        cap_groups_ = want_g;
+        ws_bytes_ = bytes;
     }
 
-    void run_chunk(const uint32_t *d_scalars, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) {
+    template <bool SCATTER>
+    void launch_digits(int src, const uint32_t *d_src, const DigitParams &dp, uint32_t dblocks, uint32_t *counters, uint32_t *pairs,
+                       cudaStream_t s) {
+        if (!dblocks) return;
+        if (src == SRC_BPOLY)
+            k_digits<SCATTER, SRC_BPOLY, S><<<dblocks, 256, 0, s>>>(d_src, dp, counters, pairs);
+        else
+            k_digits<SCATTER, SRC_MEMORY, S><<<dblocks, 256, 0, s>>>(d_src, dp, counters, pairs);
+        launches_++;
+    }
+
+    void run_chunk(int src, const uint32_t *d_src, int bpoly_k, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) {
         DigitParams dp;
         dp.n_used = n_used;
         dp.n_bases = n_bases_;
@@ -519,6 +643,8 @@ class MsmEngine : public MsmEngineBase {
         dp.W = W_;
         dp.wsep = cfg_.precompute ? 0 : 1;
         dp.nbw = nbw_;
+        dp.bpoly_k = bpoly_k;
+        dp.err = err_;
         const uint32_t groups = nmsm * (cfg_.precompute ? 1u : (uint32_t)W_);
         const uint32_t nb = groups * nbw_;
         const uint64_t nscal = (uint64_t)nmsm * n_used;
@@ -526,13 +652,15 @@ class MsmEngine : public MsmEngineBase {
         const uint32_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
 
         CUDA_OK(cudaMemsetAsync(counters_, 0, (size_t)(nb + 1) * sizeof(uint32_t), s));
-        if (dblocks) k_digits<false><<<dblocks, 256, 0, s>>>(d_scalars, dp, counters_, nullptr);
+        launch_digits<false>(src, d_src, dp, dblocks, counters_, nullptr, s);
         k_scan_tiles<<<ntiles, SCAN_THREADS, 0, s>>>(counters_, offsets_, tile_sums_, nb);
         k_scan_top<<<1, SCAN_THREADS, 0, s>>>(tile_sums_, ntiles);
         k_scan_finish<<<(nb + 1 + 255) / 256, 256, 0, s>>>(offsets_, counters_, tile_sums_, nb, ntiles);
-        if (dblocks) k_digits<true><<<dblocks, 256, 0, s>>>(d_scalars, dp, counters_, pairs_);
+        launches_ += 3;
+        launch_digits<true>(src, d_src, dp, dblocks, counters_, pairs_, s);
         if (timing_) CUDA_OK(cudaEventRecord(ev0_, s));
         k_accumulate<F><<<(nb + 127) / 128, 128, 0, s>>>(offsets_, pairs_, table_, buckets_, nb);
+        launches_++;
         if (timing_) CUDA_OK(cudaEventRecord(ev1_, s));
 
         // running-sum levels
@@ -543,11 +671,12 @@ class MsmEngine : public MsmEngineBase {
             int m = 1 << log_m_[l];
             uint32_t outN = N / m;
             uint32_t total_out = groups * outN;
-            xyzz *S = lvlS_[l & 1];
-            k_reduce_level<F><<<(total_out + 127) / 128, 128, 0, s>>>(in, S, lvlW_, total_out, m);
+            xyzz *Sl = lvlS_[l & 1];
+            k_reduce_level<F><<<(total_out + 127) / 128, 128, 0, s>>>(in, Sl, lvlW_, total_out, m);
             k_sum_points<F><<<groups, SUM_THREADS, 0, s>>>(lvlW_, sumW_ + (size_t)l * groups, outN);
-            in = S;
-            last_S = S;
+            launches_ += 2;
+            in = Sl;
+            last_S = Sl;
             N = outN;
         }
         FinalParams fp;
@@ -557,6 +686,7 @@ class MsmEngine : public MsmEngineBase {
         fp.c = cfg_.c;
         fp.groups = groups;
         k_finalize<F><<<(nmsm + 63) / 64, 64, 0, s>>>(sumW_, last_S, fp, d_out, nmsm);
+        launches_++;
         CUDA_OK(cudaGetLastError());
     }
 
@@ -566,11 +696,12 @@ class MsmEngine : public MsmEngineBase {
     int log_m_[MAX_LEVELS] = {0};
     const affine *table_ = nullptr;
     affine *table_own_ = nullptr;
-    uint32_t *counters_ = nullptr, *offsets_ = nullptr, *tile_sums_ = nullptr, *pairs_ = nullptr;
+    uint32_t *counters_ = nullptr, *offsets_ = nullptr, *tile_sums_ = nullptr, *pairs_ = nullptr, *err_ = nullptr;
     xyzz *buckets_ = nullptr, *lvlS_[2] = {nullptr, nullptr}, *lvlW_ = nullptr, *sumW_ = nullptr;
     uint64_t cap_buckets_ = 0, cap_pairs_ = 0;
     uint32_t cap_groups_ = 0;
     size_t ws_bytes_ = 0;
+    uint64_t launches_ = 0;
     bool timing_ = false;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 };

@@ -7,6 +7,8 @@
 // The committed srs/vesta.srs and srs/pallas.srs hold exactly these points (tests pin a SHA-256 of
 // the derived arrays that was checked against those files).
 #pragma once
+#include <unistd.h>
+
 #include <cstdio>
 #include <string>
 #include <thread>
@@ -96,40 +98,83 @@ Srs<B> srs_create(uint32_t depth, unsigned nthreads = 0) {
     return srs;
 }
 
-// Flat cache: magic, depth, then (depth + 1) x 64 bytes of Montgomery-form (x, y); last entry is h.
+// Pinned digests of the derived SRS (Blake2b-512 over the (depth + 1) x 64-byte Montgomery payload:
+// g[0..depth) then h).  The same points are pinned independently in tests/golden/srs_sha256.json
+// against the reference's committed srs/{vesta,pallas}.srs.  The cache file is a trust root, so it
+// is only accepted when its payload hashes to the pin compiled into this library.
+template <class B>
+inline const char *srs_pin(uint32_t depth) {
+    if (B::ID == 1 && depth == (1u << 16))
+        return "a1c1f9fab3f026a53700fcf42d67eaad8a01f1aad9c6938073764ed4f1950421d34838024998432b534d03b8a38f5a086e66ff1369eebb8797b6bab6430f9cb6";
+    if (B::ID == 0 && depth == (1u << 15))
+        return "7b928f3f7312de46acad01eb865ba564152c81eb8d2ba7d32ab7b06b055adf93c5fcd286b99b80e9219cfe4e7264614c101305a34f6d5cc63cf15a22d145e170";
+    return nullptr;  // other depths (tests, config 2) are never cached
+}
+inline std::string hex_of(const uint8_t *b, size_t n) {
+    static const char *d = "0123456789abcdef";
+    std::string s;
+    for (size_t i = 0; i < n; i++) {
+        s += d[b[i] >> 4];
+        s += d[b[i] & 15];
+    }
+    return s;
+}
+template <class B>
+std::vector<uint64_t> srs_payload(const Srs<B> &srs) {
+    std::vector<uint64_t> buf((srs.g.size() + 1) * 8);
+    for (size_t i = 0; i <= srs.g.size(); i++) {
+        const Affine<B> &p = i < srs.g.size() ? srs.g[i] : srs.h;
+        std::memcpy(&buf[i * 8], p.x.l, 32);
+        std::memcpy(&buf[i * 8 + 4], p.y.l, 32);
+    }
+    return buf;
+}
+template <class B>
+bool srs_matches_pin(const Srs<B> &srs) {
+    const char *pin = srs_pin<B>((uint32_t)srs.g.size());
+    if (!pin) return false;
+    auto buf = srs_payload(srs);
+    auto dg = Blake2b512::hash(reinterpret_cast<const uint8_t *>(buf.data()), buf.size() * 8);
+    return hex_of(dg.data(), 64) == pin;
+}
+
+// Flat cache: magic, field id, depth, 0, then the payload above.  Accepted only if the payload matches
+// the compiled-in pin; written to a temporary name and renamed so a concurrent reader never sees a
+// partial file.
 template <class B>
 bool srs_load_cache(const std::string &path, uint32_t depth, Srs<B> &out) {
+    if (!srs_pin<B>(depth)) return false;
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) return false;
     uint32_t hdr[4];
     bool ok = std::fread(hdr, sizeof hdr, 1, f) == 1 && hdr[0] == 0x53525342u && hdr[1] == (uint32_t)B::ID && hdr[2] == depth;
-    if (ok) {
-        out.g.resize(depth);
-        std::vector<uint64_t> buf((size_t)(depth + 1) * 8);
-        ok = std::fread(buf.data(), 64, depth + 1, f) == depth + 1;
-        if (ok) {
-            for (uint32_t i = 0; i <= depth; i++) {
-                Affine<B> &p = i < depth ? out.g[i] : out.h;
-                std::memcpy(p.x.l, &buf[(size_t)i * 8], 32);
-                std::memcpy(p.y.l, &buf[(size_t)i * 8 + 4], 32);
-                p.inf = false;
-            }
-        }
-    }
+    std::vector<uint64_t> buf((size_t)(depth + 1) * 8);
+    if (ok) ok = std::fread(buf.data(), 64, depth + 1, f) == depth + 1;
     std::fclose(f);
-    return ok;
+    if (!ok) return false;
+    auto dg = Blake2b512::hash(reinterpret_cast<const uint8_t *>(buf.data()), buf.size() * 8);
+    if (hex_of(dg.data(), 64) != srs_pin<B>(depth)) return false;
+    out.g.resize(depth);
+    for (uint32_t i = 0; i <= depth; i++) {
+        Affine<B> &p = i < depth ? out.g[i] : out.h;
+        std::memcpy(p.x.l, &buf[(size_t)i * 8], 32);
+        std::memcpy(p.y.l, &buf[(size_t)i * 8 + 4], 32);
+        p.inf = false;
+    }
+    return true;
 }
 template <class B>
 bool srs_store_cache(const std::string &path, const Srs<B> &srs) {
-    FILE *f = std::fopen(path.c_str(), "wb");
+    std::string tmp = path + ".tmp." + std::to_string((unsigned long)getpid());
+    FILE *f = std::fopen(tmp.c_str(), "wb");
     if (!f) return false;
     uint32_t hdr[4] = {0x53525342u, (uint32_t)B::ID, (uint32_t)srs.g.size(), 0};
-    bool ok = std::fwrite(hdr, sizeof hdr, 1, f) == 1;
-    for (size_t i = 0; ok && i <= srs.g.size(); i++) {
-        const Affine<B> &p = i < srs.g.size() ? srs.g[i] : srs.h;
-        ok = std::fwrite(p.x.l, 32, 1, f) == 1 && std::fwrite(p.y.l, 32, 1, f) == 1;
-    }
+    auto buf = srs_payload(srs);
+    bool ok = std::fwrite(hdr, sizeof hdr, 1, f) == 1 && std::fwrite(buf.data(), 8, buf.size(), f) == buf.size();
+    ok = ok && std::fflush(f) == 0 && fsync(fileno(f)) == 0;
     std::fclose(f);
+    if (ok) ok = std::rename(tmp.c_str(), path.c_str()) == 0;
+    if (!ok) std::remove(tmp.c_str());
     return ok;
 }
 

@@ -130,3 +130,239 @@ def host_blake2b512(data: bytes) -> bytes:
     out = ctypes.create_string_buffer(64)
     load().mina_b200_host_blake2b512(data, ctypes.c_size_t(len(data)), out)
     return out.raw
+
+
+# ---- verifier boundary (include/mina_verifier.h, include/mina_account_verifier.h) ---------------------
+MAX_STATE_PROOF_SIZE = 48 * 1024
+MAX_ACCOUNT_PROOF_SIZE = 16 * 1024
+MAX_PUB_INPUT_SIZE = 6 * 1024
+MODE_PER_PROOF, MODE_RLC = 0, 1
+
+STAGES = {
+    "lengths": 1 << 0, "decode_proof": 1 << 1, "decode_pub": 1 << 2, "pub_structure": 1 << 3, "pub_hashes": 1 << 4,
+    "consensus": 1 << 5, "accumulator": 1 << 6, "step_accumulators": 1 << 7, "kimchi": 1 << 8,
+    "account_abi": 1 << 9, "account_leaf": 1 << 10, "merkle": 1 << 11, "internal_error": 1 << 31,
+}
+
+
+class StageReport(ctypes.Structure):
+    _fields_ = [("passed", ctypes.c_uint32), ("failed", ctypes.c_uint32), ("unavailable", ctypes.c_uint32)]
+
+    def names(self, mask):
+        return sorted(k for k, v in STAGES.items() if mask & v)
+
+    def as_dict(self):
+        return {"passed": self.names(self.passed), "failed": self.names(self.failed), "unavailable": self.names(self.unavailable)}
+
+
+def _padded(data: bytes, size: int):
+    """The fixed-size zero-padded array the Go operator / Rust batcher pass (operator.go:534-541)."""
+    buf = (ctypes.c_ubyte * max(size, len(data)))()
+    ctypes.memmove(buf, data, len(data))
+    return buf
+
+
+def verify_mina_state(proof: bytes, pub: bytes, proof_len: int | None = None, pub_len: int | None = None) -> bool:
+    """Mirror of AL/operator/mina/mina.go:27-32 VerifyMinaState."""
+    lib = load()
+    lib.verify_mina_state_ffi.restype = ctypes.c_bool
+    lib.verify_mina_state_ffi.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+    pb, ib = _padded(proof, MAX_STATE_PROOF_SIZE), _padded(pub, MAX_PUB_INPUT_SIZE)
+    return bool(lib.verify_mina_state_ffi(pb, len(proof) if proof_len is None else proof_len, ib, len(pub) if pub_len is None else pub_len))
+
+
+def verify_account_inclusion(proof: bytes, pub: bytes, proof_len: int | None = None, pub_len: int | None = None) -> bool:
+    """Mirror of AL/operator/mina_account/mina_account.go:27-32 VerifyAccountInclusion."""
+    lib = load()
+    lib.verify_account_inclusion_ffi.restype = ctypes.c_bool
+    lib.verify_account_inclusion_ffi.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+    pb, ib = _padded(proof, MAX_ACCOUNT_PROOF_SIZE), _padded(pub, MAX_PUB_INPUT_SIZE)
+    return bool(lib.verify_account_inclusion_ffi(pb, len(proof) if proof_len is None else proof_len, ib, len(pub) if pub_len is None else pub_len))
+
+
+def last_stages() -> StageReport:
+    rep = StageReport()
+    load().mina_b200_last_stages(ctypes.byref(rep))
+    return rep
+
+
+class Batch:
+    """Pointer / length arrays over a list of byte strings (kept alive with the object)."""
+
+    def __init__(self, items):
+        self.n = len(items)
+        self.keep = [ctypes.create_string_buffer(bytes(x), max(len(x), 1)) for x in items]
+        self.ptrs = (ctypes.c_void_p * max(self.n, 1))(*[ctypes.addressof(b) for b in self.keep])
+        self.lens = (ctypes.c_size_t * max(self.n, 1))(*[len(x) for x in items])
+
+
+def verify_state_stages(proofs, pubs, mode: int = MODE_RLC):
+    """Batch verifier with per-proof stage reports: returns (accept bits, [StageReport])."""
+    p, q = (proofs if isinstance(proofs, Batch) else Batch(proofs)), (pubs if isinstance(pubs, Batch) else Batch(pubs))
+    reports = (StageReport * max(p.n, 1))()
+    accept = (ctypes.c_uint8 * max(p.n, 1))()
+    lib = load()
+    lib.mina_b200_verify_state_stages.argtypes = [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    _check(lib.mina_b200_verify_state_stages(p.n, p.ptrs, p.lens, q.ptrs, q.lens, mode, reports, accept))
+    return list(accept[: p.n]), list(reports[: p.n])
+
+
+def verify_state_batch(proofs, pubs):
+    p, q = (proofs if isinstance(proofs, Batch) else Batch(proofs)), (pubs if isinstance(pubs, Batch) else Batch(pubs))
+    accept = (ctypes.c_uint8 * max(p.n, 1))()
+    lib = load()
+    lib.verify_mina_state_batch_ffi.argtypes = [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    rc = lib.verify_mina_state_batch_ffi(p.n, p.ptrs, p.lens, q.ptrs, q.lens, accept)
+    if rc != 0:
+        raise MinaB200Error(load().mina_b200_last_error().decode() or "batch verify failed")
+    return list(accept[: p.n])
+
+
+def verify_account_stages(proofs, pubs):
+    p, q = Batch(proofs), Batch(pubs)
+    reports = (StageReport * max(p.n, 1))()
+    accept = (ctypes.c_uint8 * max(p.n, 1))()
+    lib = load()
+    lib.mina_b200_verify_account_stages.argtypes = [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p]
+    _check(lib.mina_b200_verify_account_stages(p.n, p.ptrs, p.lens, q.ptrs, q.lens, reports, accept))
+    return list(accept[: p.n]), list(reports[: p.n])
+
+
+def accumulator_check(proofs, mode: int = MODE_PER_PROOF):
+    """accumulator_check from raw proof bytes: [(wrap_ok, step0_ok, step1_ok)] per proof."""
+    p = proofs if isinstance(proofs, Batch) else Batch(proofs)
+    ok = (ctypes.c_uint8 * max(3 * p.n, 1))()
+    lib = load()
+    lib.mina_b200_accumulator_check_batch.argtypes = [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    _check(lib.mina_b200_accumulator_check_batch(p.n, p.ptrs, p.lens, mode, ok))
+    return [tuple(ok[3 * i : 3 * i + 3]) for i in range(p.n)]
+
+
+# ---- K4 / K2 / K5 / K3 hooks ----------------------------------------------------------------------------
+def endo_to_field(field: int, pre: bytes) -> bytes:
+    n = len(pre) // 16
+    out = ctypes.create_string_buffer(32 * max(n, 1))
+    _check(load().mina_b200_endo_to_field(field, ctypes.c_uint32(n), pre, out))
+    return out.raw[: 32 * n]
+
+
+def bpoly_coeffs(field: int, chals: bytes, k: int) -> bytes:
+    nproofs = len(chals) // (32 * k)
+    out = ctypes.create_string_buffer((32 << k) * max(nproofs, 1))
+    _check(load().mina_b200_bpoly_coeffs(field, ctypes.c_uint32(nproofs), k, chals, out))
+    return out.raw[: (32 << k) * nproofs]
+
+
+def bpoly_combine(field: int, chals: bytes, r: bytes, k: int) -> bytes:
+    nproofs = len(r) // 32
+    out = ctypes.create_string_buffer(32 << k)
+    _check(load().mina_b200_bpoly_combine(field, ctypes.c_uint32(nproofs), k, chals, r, out))
+    return out.raw
+
+
+def bpoly_eval(field: int, chals: bytes, xs: bytes, k: int, npts: int) -> bytes:
+    nproofs = len(chals) // (32 * k)
+    out = ctypes.create_string_buffer(32 * max(nproofs * npts, 1))
+    _check(load().mina_b200_bpoly_eval(field, ctypes.c_uint32(nproofs), ctypes.c_uint32(npts), k, chals, xs, out))
+    return out.raw[: 32 * nproofs * npts]
+
+
+def poseidon_permute(field: int, table: bytes, states: bytes) -> bytes:
+    n = len(states) // 96
+    buf = ctypes.create_string_buffer(states, max(len(states), 1))
+    _check(load().mina_b200_poseidon_permute(field, table, ctypes.c_uint32(n), buf))
+    return buf.raw[: 96 * n]
+
+
+def merkle_fold(table: bytes, paths, leaves, roots):
+    """paths: list of [(tag, sibling_int)]; returns ([ok], [folded root int])."""
+    n = len(paths)
+    max_depth = max([len(p) for p in paths] + [1])
+    depths = (ctypes.c_uint32 * n)(*[len(p) for p in paths])
+    tags = bytearray(n * max_depth)
+    sib = bytearray(32 * n * max_depth)
+    for i, p in enumerate(paths):
+        for d, (tag, h) in enumerate(p):
+            tags[i * max_depth + d] = tag
+            sib[32 * (i * max_depth + d) : 32 * (i * max_depth + d) + 32] = int(h).to_bytes(32, "little")
+    lv = b"".join(int(x).to_bytes(32, "little") for x in leaves)
+    rt = b"".join(int(x).to_bytes(32, "little") for x in roots)
+    ok = ctypes.create_string_buffer(n)
+    folded = ctypes.create_string_buffer(32 * n)
+    _check(load().mina_b200_merkle_fold(table, ctypes.c_uint32(n), ctypes.c_uint32(max_depth), depths, bytes(tags), bytes(sib), lv, rt, ok, folded))
+    return [b for b in ok.raw], [int.from_bytes(folded.raw[32 * i : 32 * i + 32], "little") for i in range(n)]
+
+
+def poseidon_trusted() -> bool:
+    return bool(load().mina_b200_poseidon_trusted())
+
+
+# ---- host-only hooks --------------------------------------------------------------------------------------
+class WireSummary(ctypes.Structure):
+    _fields_ = [
+        ("consumed", ctypes.c_uint64), ("proof_end", ctypes.c_uint64),
+        ("n_step_comms", ctypes.c_uint32), ("n_lr", ctypes.c_uint32), ("merkle_depth", ctypes.c_uint32), ("is_devnet", ctypes.c_uint32),
+        ("blockchain_length", ctypes.c_uint32 * 17), ("curr_global_slot", ctypes.c_uint32 * 17),
+        ("epoch_count", ctypes.c_uint32 * 17), ("min_window_density", ctypes.c_uint32 * 17),
+        ("state_begin", ctypes.c_uint64 * 17), ("state_end", ctypes.c_uint64 * 17),
+        ("previous_state_hash", (ctypes.c_uint8 * 32) * 17), ("first_pass_ledger", (ctypes.c_uint8 * 32) * 17),
+        ("wrap_sg", ctypes.c_uint8 * 64), ("step_sg", (ctypes.c_uint8 * 64) * 2), ("hash0", ctypes.c_uint8 * 32),
+        ("encoded_account_len", ctypes.c_uint64), ("balance", ctypes.c_uint64), ("nonce", ctypes.c_uint32), ("has_zkapp", ctypes.c_uint32),
+    ]
+
+
+def host_decode(kind: int, data: bytes):
+    """kind: 0 state proof, 1 state pub, 2 account proof, 3 account pub.  None on a decode error."""
+    s = WireSummary()
+    lib = load()
+    lib.mina_b200_host_decode.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
+    rc = lib.mina_b200_host_decode(kind, data, len(data), ctypes.byref(s))
+    return s if rc == 0 else None
+
+
+def host_select_secure_chain(candidate: bytes, tip: bytes) -> int:
+    """1 = Candidate, 0 = Bridge; raises on the reference's Err / undecodable input."""
+    res = ctypes.c_int(-1)
+    lib = load()
+    lib.mina_b200_host_select_secure_chain.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
+    rc = lib.mina_b200_host_select_secure_chain(candidate, len(candidate), tip, len(tip), ctypes.byref(res))
+    if rc != 0:
+        raise MinaB200Error({-1: "decode error", -2: "constants differ", -3: "needs state hash"}.get(rc, "error %d" % rc))
+    return res.value
+
+
+def host_vk_load(path: str):
+    out = ctypes.create_string_buffer(28 * 64 + 14 * 32)
+    meta = (ctypes.c_uint32 * 4)()
+    rc = load().mina_b200_host_vk_load(path.encode(), out, meta)
+    if rc != 0:
+        raise MinaB200Error(load().mina_b200_last_error().decode())
+    raw = out.raw
+    ints = lambda off, n: [int.from_bytes(raw[off + 32 * i : off + 32 * i + 32], "little") for i in range(n)]
+    comms = [(int.from_bytes(raw[64 * i : 64 * i + 32], "little"), int.from_bytes(raw[64 * i + 32 : 64 * i + 64], "little")) for i in range(28)]
+    o = 28 * 64
+    return {
+        "commitments": comms, "shifts": ints(o, 7), "group_gen": ints(o + 7 * 32, 1)[0], "zk_w3": ints(o + 8 * 32, 1)[0],
+        "zkpm": ints(o + 9 * 32, 4), "endo": ints(o + 13 * 32, 1)[0],
+        "log_size_of_group": meta[0], "max_poly_size": meta[1], "public": meta[2], "prev_challenges": meta[3],
+    }
+
+
+def host_hash_with_kimchi(table: bytes, prefix: str, xs) -> int:
+    out = ctypes.create_string_buffer(32)
+    data = b"".join(int(x).to_bytes(32, "little") for x in xs)
+    rc = load().mina_b200_host_hash_with_kimchi(table, prefix.encode(), data, ctypes.c_uint32(len(xs)), out)
+    if rc != 0:
+        raise MinaB200Error("host_hash_with_kimchi failed: %d" % rc)
+    return int.from_bytes(out.raw, "little")
+
+
+def host_poseidon_permute(field: int, table: bytes, states: bytes) -> bytes:
+    n = len(states) // 96
+    buf = ctypes.create_string_buffer(states, max(len(states), 1))
+    rc = load().mina_b200_host_poseidon_permute(field, table, ctypes.c_uint32(n), buf)
+    if rc != 0:
+        raise MinaB200Error("host_poseidon_permute failed: %d" % rc)
+    return buf.raw[: 96 * n]

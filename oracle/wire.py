@@ -358,3 +358,64 @@ def decode_account_pub(data: bytes):
     out["encoded_account"] = c.bytestr()
     out["_consumed"] = c.o
     return out
+
+
+# ---- producer side: re-encode a decoded protocol state (bincode), used to build mutated test vectors the
+# way the reference's consensus tests mutate the fixture (consensus_state.rs:197-303) -------------------------
+def _w_bigint(x: int) -> bytes:
+    return struct.pack("<Q", 32) + int(x).to_bytes(32, "little")
+
+
+def _w_bytes(b: bytes) -> bytes:
+    return struct.pack("<Q", len(b)) + bytes(b)
+
+
+def _w_signed(a) -> bytes:
+    return struct.pack("<QI", a[0], a[1])
+
+
+def _w_registers(r) -> bytes:
+    ls = r["local_state"]
+    out = _w_bigint(r["first_pass_ledger"]) + _w_bigint(r["second_pass_ledger"])
+    pcs = r["pending_coinbase_stack"]
+    out += _w_bigint(pcs["data"]) + _w_bigint(pcs["state_init"]) + _w_bigint(pcs["state_curr"])
+    out += _w_bigint(ls["stack_frame"]) + _w_bigint(ls["call_stack"]) + _w_bigint(ls["transaction_commitment"])
+    out += _w_bigint(ls["full_transaction_commitment"]) + _w_signed(ls["excess"]) + _w_signed(ls["supply_increase"])
+    out += _w_bigint(ls["ledger"]) + struct.pack("<BI", int(ls["success"]), ls["account_update_index"])
+    out += struct.pack("<Q", len(ls["failure_status_tbl"]))
+    for row in ls["failure_status_tbl"]:
+        out += struct.pack("<Q", len(row)) + b"".join(struct.pack("<I", t) for t in row)
+    return out + struct.pack("<B", int(ls["will_succeed"]))
+
+
+def _w_epoch(e) -> bytes:
+    return (_w_bigint(e["ledger_hash"]) + struct.pack("<Q", e["ledger_total_currency"]) + _w_bigint(e["seed"])
+            + _w_bigint(e["start_checkpoint"]) + _w_bigint(e["lock_checkpoint"]) + struct.pack("<I", e["epoch_length"]))
+
+
+def _w_pubkey(k) -> bytes:
+    return _w_bigint(k[0]) + struct.pack("<B", int(k[1]))
+
+
+def encode_protocol_state(st) -> bytes:
+    body = st["body"]
+    bs, cs, k = body["blockchain_state"], body["consensus_state"], body["constants"]
+    slh, lps = bs["staged_ledger_hash"], bs["ledger_proof_statement"]
+    out = _w_bigint(st["previous_state_hash"]) + _w_bigint(body["genesis_state_hash"])
+    out += _w_bigint(slh["ledger_hash"]) + _w_bytes(slh["aux_hash"]) + _w_bytes(slh["pending_coinbase_aux"]) + _w_bigint(slh["pending_coinbase_hash"])
+    out += _w_bigint(bs["genesis_ledger_hash"]) + _w_registers(lps["source"]) + _w_registers(lps["target"])
+    out += _w_bigint(lps["connecting_ledger_left"]) + _w_bigint(lps["connecting_ledger_right"]) + _w_signed(lps["supply_increase"])
+    for tok, amt in lps["fee_excess"]:
+        out += _w_bigint(tok) + _w_signed(amt)
+    out += struct.pack("<Q", bs["timestamp"]) + _w_bytes(bs["body_reference"])
+    out += struct.pack("<III", cs["blockchain_length"], cs["epoch_count"], cs["min_window_density"])
+    out += struct.pack("<Q", len(cs["sub_window_densities"])) + b"".join(struct.pack("<I", d) for d in cs["sub_window_densities"])
+    out += _w_bytes(cs["last_vrf_output"]) + struct.pack("<Q", cs["total_currency"])
+    out += struct.pack("<III", 0, cs["curr_global_slot"]["slot_number"], cs["curr_global_slot"]["slots_per_epoch"])
+    out += struct.pack("<II", 0, cs["global_slot_since_genesis"])
+    out += _w_epoch(cs["staking_epoch_data"]) + _w_epoch(cs["next_epoch_data"])
+    out += struct.pack("<B", int(cs["has_ancestor_in_same_checkpoint_window"]))
+    out += _w_pubkey(cs["block_stake_winner"]) + _w_pubkey(cs["block_creator"]) + _w_pubkey(cs["coinbase_receiver"])
+    out += struct.pack("<B", int(cs["supercharge_coinbase"]))
+    out += struct.pack("<IIIIIQ", k["k"], k["slots_per_epoch"], k["slots_per_sub_window"], k["grace_period_slots"], k["delta"], k["genesis_state_timestamp"])
+    return out

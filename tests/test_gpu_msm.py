@@ -124,8 +124,8 @@ def test_msm_generic_bases_windows(gpu, cid, c):
 
 
 def test_accumulator_kats_on_gpu(gpu, state_proof):
-    # K-A, K-B, K-C through the CUDA path (scalars prepared by the oracle here; the device
-    # b_poly/endo kernels have their own tests)
+    # K-A, K-B, K-C with ORACLE-prepared scalars: pins the MSM engine alone.  The full row (device endo +
+    # b_poly + MSM from raw proof bytes) is tests/test_gpu_verifier.py::test_accumulator_check_*.
     pr = state_proof["candidate_tip_proof"]
     pre = b"".join(x.to_bytes(16, "little") for x in pr["bulletproof_challenges"])
     s = cref.bpoly_coeffs(cref.FP, cref.endo_to_field(cref.FP, pre, pasta.ENDO_FP))
