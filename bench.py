@@ -1,12 +1,24 @@
 #!/usr/bin/env python3
 """bench.py -- one JSON line per run (driver contract).
 
-WHAT THIS MEASURES TODAY (read DESIGN.md section 0): a "step" is one batch of per-proof
-accumulator-check MSMs -- <b_poly-sized scalars, vesta.srs.g[0..65536)>, SURVEY row a7, the dominant
-loop of `verify_block` (AL/operator/mina/lib/src/lib.rs:99-111) -- one MSM per proof.  That stage is
-parity-pinned (KAT K-A).  It is NOT "proofs verified/s": the Fiat-Shamir transcript, Poseidon and the
-IPA scalar preparation are not built (Poseidon constants unavailable => parity unpinned), so the
-metric is named for the stage and `config.absent_stages` says what is missing.
+Default workload `state1024` (BASELINE.json: "1024-proof Mina-state batch"): one STEP verifies a fixed
+batch of 1024 serialized proof-of-state inputs (the reference's own fixture replicated, 1 % of them
+with one flipped bit in an IPA prechallenge) through every stage this build has -- bincode decode,
+the plain-comparison half of check_pub_inputs, the fork-choice rule, accumulator_check (Vesta 2^16)
+and the wrap proof's two previous-challenge accumulators (Pallas 2^15).  The batch is strong-scaled:
+rank r takes proofs i = r (mod N); the per-proof result bytes are combined with ONE NCCL
+all-reduce(MIN) inside the timed region (AL/operator/pkg/operator.go:461-465).
+
+READ `config.absent_stages`: the kimchi transcript / IPA final check and the 17 Poseidon state hashes
+are NOT built (Poseidon constants unavailable => parity unpinned), so the full
+accept bit is always 0 and the byte that is reduced is "every built stage passed".  The metric is named
+for what it is.
+
+  value  = proofs/s with the per-proof device inputs (prechallenges + accumulator points) resident in HBM
+  e2e    = proofs/s through the C ABI with HOST buffers holding the serialized proofs (decode on host
+           threads, pinned staging, H2D, kernels, D2H of the result bytes all inside the timed region)
+Other workloads: --workload msm20 (BASELINE config 2: one 2^20-point Vesta MSM over resident bases),
+--workload accmsm (round-1 line: 64 per-proof 2^16 MSMs with uploaded scalars).
 """
 from __future__ import annotations
 
@@ -21,13 +33,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_POINTS = 65536          # Vesta accumulator check
-BATCH = 64                # MSMs (= proofs) per step per GPU; 64 x 2 MiB scalars = 128 MiB > L2 (126 MB)
+BATCH = 1024              # proofs per step, whole job (BASELINE.json configs[3] / north_star target)
+CORRUPT_EVERY = 101       # proofs i with i % 101 == 7 get one flipped prechallenge bit (10 of 1024)
 ALG_BYTES_PER_POINT = 96  # 64 B affine base + 32 B scalar
-METRIC = "accumulator_check_msm_per_sec"
-UNIT = "MSM/s (n=65536, Vesta)"
-ABSENT = ["fiat_shamir_transcript", "poseidon_sponge (constants unavailable, parity unpinned)",
-          "ipa_final_check_scalars", "protocol_state_hashing", "accept_bit"]
+OFF_WRAP_PRE, OFF_WRAP_X, OFF_WRAP_Y = 73, 374, 414
+OFF_STEP_PRE, OFF_STEP_SG = 446, 934
+ABSENT = ["kimchi to_batch + IPA final check (Fiat-Shamir needs Poseidon)", "17 Poseidon protocol-state hashes",
+          "full accept bit (always 0 until the two stages above exist)"]
+BUILT = ["bincode decode", "check_pub_inputs: ledger-hash + to_fp comparisons", "select_secure_chain",
+         "accumulator_check (Vesta MSM 2^16, K-A pinned)", "wrap prev-challenge accumulators (2 x Pallas MSM 2^15, K-B/K-C pinned)"]
 
 
 def peaks():
@@ -61,50 +75,313 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
 
 
-def synth_scalars_host(nmsm: int, seed: int) -> bytes:
-    """Uniform 253-bit scalars (canonical, < p) from a fixed-seed generator."""
+def golden(name):
+    return open(os.path.join(ROOT, "tests", "golden", name), "rb").read()
+
+
+def synth_batch():
+    """The fixed 1024-proof batch: (proofs, pubs, expected built-stage bit)."""
+    proof, pub = golden("mina_state.proof"), golden("mina_state.pub")
+    proofs, want = [], []
+    for i in range(BATCH):
+        if i % CORRUPT_EVERY == 7:
+            m = bytearray(proof)
+            m[OFF_WRAP_PRE + (i % 256)] ^= 1 << (i % 8)
+            proofs.append(bytes(m))
+            want.append(0)
+        else:
+            proofs.append(proof)
+            want.append(1)
+    return proofs, [pub] * BATCH, want
+
+
+def device_inputs(proofs, torch, dev):
+    """What the host pass extracts from each proof, packed as the device arrays the kernels read."""
     import numpy as np
 
-    rng = np.random.default_rng(seed)
-    a = rng.integers(0, 1 << 32, size=(nmsm, N_POINTS, 8), dtype=np.uint32)
-    a[:, :, 7] &= 0x1FFFFFFF
-    return a.tobytes()
+    pre_w = b"".join(p[OFF_WRAP_PRE:OFF_WRAP_PRE + 256] for p in proofs)
+    pts_w = b"".join(p[OFF_WRAP_X:OFF_WRAP_X + 32] + p[OFF_WRAP_Y:OFF_WRAP_Y + 32] for p in proofs)
+    pre_s = b"".join(p[OFF_STEP_PRE:OFF_STEP_PRE + 480] for p in proofs)
+    pts_s = b"".join(p[OFF_STEP_SG + 80 * k + 8:OFF_STEP_SG + 80 * k + 40] + p[OFF_STEP_SG + 80 * k + 48:OFF_STEP_SG + 80 * k + 80]
+                     for p in proofs for k in range(2))
+    to_dev = lambda b: torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).to(dev)
+    return to_dev(pre_w), to_dev(pts_w), to_dev(pre_s), to_dev(pts_s)
 
 
-def cpu_sample(threads: int, nmsm: int):
-    from oracle import cref
+# ---- CPU side: the oracle port doing the same per-proof work the reference does (one MSM per accumulator) ----
+def cpu_verify_sample(proofs, pubs, threads):
+    from oracle import cref, pasta, wire
 
     cref.build()
-    bases, _ = cref.srs_derive(cref.FQ, 0, N_POINTS, False)
-    sc = synth_scalars_host(nmsm, 99)
+    bases_v = cpu_verify_sample.cache.get("v")
+    if bases_v is None:
+        bases_v, _ = cref.srs_derive(cref.FQ, 0, 65536, False)
+        bases_p, _ = cref.srs_derive(cref.FP, 0, 32768, False)
+        cpu_verify_sample.cache.update(v=bases_v, p=bases_p)
+    bases_p = cpu_verify_sample.cache["p"]
     t0 = time.perf_counter()
-    for k in range(nmsm):
-        cref.msm(cref.FQ, sc[k * N_POINTS * 32:(k + 1) * N_POINTS * 32], bases, threads)
-    return nmsm / (time.perf_counter() - t0)
+    bits = []
+    for pb, qb in zip(proofs, pubs):
+        sp, sq = wire.decode_state_proof(pb), wire.decode_state_pub(qb)
+        ok = all(sq["candidate_chain_ledger_hashes"][i] ==
+                 sp["candidate_chain_states"][i]["body"]["blockchain_state"]["ledger_proof_statement"]["target"]["first_pass_ledger"]
+                 for i in range(16))
+        pr = sp["candidate_tip_proof"]
+        pre = b"".join(x.to_bytes(16, "little") for x in pr["bulletproof_challenges"])
+        s = cref.bpoly_coeffs(cref.FP, cref.endo_to_field(cref.FP, pre, pasta.ENDO_FP))
+        got, _ = cref.msm(cref.FQ, s, bases_v, threads)
+        ok = ok and cref.bytes_to_point(got) == pr["wrap_challenge_polynomial_commitment"]
+        for k in range(2):
+            pre = b"".join(x.to_bytes(16, "little") for x in pr["wrap_old_bulletproof_challenges"][k])
+            s = cref.bpoly_coeffs(cref.FQ, cref.endo_to_field(cref.FQ, pre, pasta.ENDO_FQ))
+            got, _ = cref.msm(cref.FP, s, bases_p, threads)
+            ok = ok and cref.bytes_to_point(got) == pr["step_challenge_polynomial_commitments"][k]
+        bits.append(int(ok))
+    return len(proofs) / (time.perf_counter() - t0), bits
+
+
+cpu_verify_sample.cache = {}
+METRIC = "mina_state_proofs_per_sec_built_stages"
+UNIT = "proofs/s"
 
 
 def run_reference(a):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    vals = []
+    proofs, pubs, want = synth_batch()
+    sample = 2
+    cpu_verify_sample(proofs[:1], pubs[:1], cores)  # builds the library and the SRS outside the timed steps
     for _ in range(a.warmup):
-        cpu_sample(cores, 1)
+        cpu_verify_sample(proofs[:1], pubs[:1], cores)
+    vals = []
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        vals.append(cpu_sample(cores, 2))
+    for s in range(a.steps):
+        lo = (7 + s * sample) % (BATCH - sample)  # slides over the batch, includes corrupted members
+        v, bits = cpu_verify_sample(proofs[lo:lo + sample], pubs[lo:lo + sample], cores)
+        assert bits == want[lo:lo + sample]
+        vals.append(v)
     dt = time.perf_counter() - t0
     v = sum(vals) / len(vals)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u256 modular (4x64 Montgomery)", "data": "synthetic",
-        "config": {"workload": "per-proof accumulator-check MSM, n=65536 Vesta", "absent_stages": ABSENT},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u256 modular (4x64 Montgomery)", "data": "synthetic",
+        "config": {"workload": "state1024: the same 1024-proof batch, per-proof accumulator MSMs like the reference (verify_block per proof)",
+                   "built_stages": BUILT, "absent_stages": ABSENT},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "2 MSMs per step; C restatement of arkworks' bucket MSM (oracle/pasta_ref.c), NOT the reference binary (unbuildable here)"},
+                         "sample": "%d proofs per step out of the 1024-proof batch; C restatement of arkworks' bucket MSM (oracle/pasta_ref.c, c = ln n + 2, one thread per window) + Python bincode decoder; NOT the reference binary (no Rust toolchain)" % sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ---- the B200 arm -------------------------------------------------------------------------------------------------
+def bench_state(a, torch, dist, mb, rank, world, dev):
+    import numpy as np
+
+    proofs, pubs, want = synth_batch()
+    mine = list(range(rank, BATCH, world))
+    my_proofs, my_pubs = [proofs[i] for i in mine], [pubs[i] for i in mine]
+    m = len(mine)
+    d_pre_w, d_pts_w, d_pre_s, d_pts_s = device_inputs(my_proofs, torch, dev)
+    idx = torch.tensor(mine, dtype=torch.int64, device=dev)
+    result = torch.ones(BATCH, dtype=torch.uint8, device=dev)
+    pin = torch.empty(m, dtype=torch.uint8).pin_memory()
+
+    def reduce_bits(bits):
+        """per-proof result bytes -> the batch vector every rank ends up with (operator.go:461-465)"""
+        pin.copy_(torch.frombuffer(bytearray(bits), dtype=torch.uint8))
+        result.fill_(1)
+        result[idx] = pin.to(dev, non_blocking=True)
+        if world > 1:
+            dist.all_reduce(result, op=dist.ReduceOp.MIN)
+        return result
+
+    def step_device(mode, timing=False):
+        a1 = mb.accumulators_device(mb.CURVE_VESTA, m, d_pre_w.data_ptr(), d_pts_w.data_ptr(), mode, timing)
+        a2 = mb.accumulators_device(mb.CURVE_PALLAS, 2 * m, d_pre_s.data_ptr(), d_pts_s.data_ptr(), mode, timing)
+        ok_w, ok_s = (a1[0], a2[0]) if timing else (a1, a2)
+        bits = bytes(ok_w[i] & ok_s[2 * i] & ok_s[2 * i + 1] for i in range(m))
+        reduce_bits(bits)
+        return (a1[1], a2[1]) if timing else None
+
+    built = 0
+    for k in ("lengths", "decode_proof", "decode_pub", "pub_structure", "consensus", "accumulator", "step_accumulators"):
+        built |= mb.STAGES[k]
+    hp, hq = mb.Batch(my_proofs), mb.Batch(my_pubs)
+
+    def step_e2e(mode):
+        _, reps = mb.verify_state_stages(hp, hq, mode)
+        bits = bytes(int(r.failed == 0 and (r.passed & built) == built) for r in reps)
+        return reduce_bits(bits)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        extra = [fn() for _ in range(steps)]
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        # the library drains its own stream before each call returns, so host wall time between the two
+        # events IS the device-inclusive time; take the max of both clocks, then the max over ranks
+        t = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), extra
+
+    W = max(a.warmup, 3)
+    expect = torch.tensor(want, dtype=torch.uint8, device=dev)
+    for mode in (mb.MODE_RLC, mb.MODE_PER_PROOF):  # correctness gate before any timing
+        step_device(mode)
+        assert torch.equal(result, expect), "device leg: result bytes differ from the expected bits"
+    assert torch.equal(step_e2e(mb.MODE_RLC), expect), "e2e leg: result bytes differ from the expected bits"
+    for _ in range(W):
+        step_device(mb.MODE_RLC)
+        step_e2e(mb.MODE_RLC)
+    sampler = ClockSampler()
+    sampler.start()
+    l0 = mb.launch_count()
+    t_dev, kms = timed(lambda: step_device(mb.MODE_RLC, True), a.steps)
+    launches = mb.launch_count() - l0
+    t_e2e, _ = timed(lambda: step_e2e(mb.MODE_RLC), a.steps)
+    pp_steps = max(2, min(a.steps, 4))
+    t_pp, kms_pp = timed(lambda: step_device(mb.MODE_PER_PROOF, True), pp_steps)
+    t_pp_e2e, _ = timed(lambda: step_e2e(mb.MODE_PER_PROOF), pp_steps)
+    sampler.stop.set()
+    sampler.join()
+    if rank != 0:
+        return None
+    peak, which = peaks()
+    # dominant kernel of the default (RLC) mode: k_bpoly_combine.  Algorithmic bytes per launch = the
+    # proofs' product tables it reads (16 KiB each) + the 2^k x 32 B combined vector it writes.
+    comb_ms = sum(k[0][1] + k[1][1] for k in kms) / a.steps
+    comb_bytes = (m * 16384 + (32 << 16)) + (2 * m * 16384 + (32 << 15))
+    comb_modmul = m * 65536 + 2 * m * 32768
+    # per-proof mode: k_accumulate, same formula as round 1 (96 B per MSM point)
+    acc_ms = sum(k[0][0] + k[1][0] for k in kms_pp) / pp_steps
+    acc_bytes = ALG_BYTES_PER_POINT * (m * 65536 + 2 * m * 32768)
+    cores = os.cpu_count() or 1
+    cpu, _ = cpu_verify_sample(proofs[6:8], pubs[6:8], cores)
+    return {
+        "metric": METRIC, "value": BATCH * a.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
+        "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u256 modular (8x32 Montgomery)", "data": "synthetic",
+        "config": {"workload": "state1024: 1024 serialized proof-of-state inputs per step (reference fixture x1024, 10 with a flipped prechallenge bit), rank r takes i = r mod N, one NCCL all-reduce(MIN) of 1024 result bytes per step",
+                   "mode": "rlc (random linear combination over the shard + bisection; per-proof numbers in `per_proof_mode`)",
+                   "built_stages": BUILT, "absent_stages": ABSENT,
+                   "l2": "per-step working set: %d x 16 KiB product tables + 64 MiB / 32 MiB fixed-base tables > 126 MB L2 together; inputs differ per proof only in 10 members" % (3 * m)},
+        "roofline": {"bound": "hbm", "achieved": comb_bytes / (comb_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": comb_bytes / (comb_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_bpoly_combine", "peak_source": which,
+                     "ms_per_step_in_kernel": comb_ms,
+                     "note": "integer-issue-bound: %.3g modmul/s in this kernel (see profiles/ for the measured modmul ceiling)" % (comb_modmul / (comb_ms * 1e-3))},
+        "per_proof_mode": {"value": BATCH * pp_steps / t_pp, "e2e": BATCH * pp_steps / t_pp_e2e, "unit": UNIT, "steps": pp_steps,
+                           "roofline": {"bound": "hbm", "achieved": acc_bytes / (acc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                        "frac": acc_bytes / (acc_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_accumulate",
+                                        "ms_per_step_in_kernel": acc_ms,
+                                        "note": "96 B x MSM points / k_accumulate CUDA-event time (round-1 formula); modmul/s = %.3g" % (10 * 16 * (m * 65536 + 2 * m * 32768) / (acc_ms * 1e-3))}},
+        "cpu_baseline": {"value": cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "2 proofs of the batch, per-proof MSMs; oracle/pasta_ref.c (arkworks window rule, 1 thread/window) + Python decoder; not the reference binary"},
+        "e2e": {"value": BATCH * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": m * (256 + 64 + 480 + 128 + 3 * 32) + m,
+                "d2h_bytes_per_step": 2 * 128 + BATCH,
+                "note": "host buffers = %d x 48 342 B serialized proofs + 1 057 B pub inputs read by host threads; only the extracted prechallenges / points / RLC scalars cross PCIe" % m},
+        "gpu_launches": int(launches), "clocks": sampler.summary(),
+    }
+
+
+def splitmix_scalars(n, seed=0x4D494E41):
+    """SplitMix64, 4 draws per scalar, reduced mod p (vectorised)."""
+    import numpy as np
+
+    P = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
+    idx = np.arange(1, 4 * n + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    limbs = z.reshape(n, 4)
+    out = bytearray()
+    for row in limbs:
+        v = (int(row[0]) | int(row[1]) << 64 | int(row[2]) << 128 | int(row[3]) << 192) % P
+        out += v.to_bytes(32, "little")
+    return bytes(out)
+
+
+def bench_msm20(a, torch, dist, mb, rank, world, dev):
+    import numpy as np
+
+    n = 1 << 20
+    pts = mb.srs_points(mb.CURVE_VESTA, 0, 65536) + mb.host_srs_derive(mb.CURVE_VESTA, 65536, n - 65536)
+    mb.fixed_base_load(mb.CURVE_VESTA, pts, 20)
+    sc = splitmix_scalars(n, 0x4D494E41 + rank)
+    d_sc = torch.from_numpy(np.frombuffer(sc, dtype=np.uint8).copy()).to(dev)
+    d_out = torch.zeros(64, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(a.warmup, 3)
+    for _ in range(W):
+        mb.fixed_base_msm_device(mb.CURVE_VESTA, 1, d_sc.data_ptr(), d_out.data_ptr(), stream)
+    l0 = mb.launch_count()
+    sampler = ClockSampler()
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    acc_ms = 0.0
+    for _ in range(a.steps):
+        acc_ms += mb.fixed_base_msm_device(mb.CURVE_VESTA, 1, d_sc.data_ptr(), d_out.data_ptr(), stream, True)
+    e1.record()
+    barrier()
+    launches = mb.launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for _ in range(2):
+        mb.fixed_base_msm(mb.CURVE_VESTA, sc, n)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        mb.fixed_base_msm(mb.CURVE_VESTA, sc, n)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    sampler.stop.set()
+    sampler.join()
+    if rank != 0:
+        return None
+    from oracle import cref
+
+    peak, which = peaks()
+    t0 = time.perf_counter()
+    cref.msm(cref.FQ, sc, pts, os.cpu_count() or 1)
+    cpu = 1.0 / (time.perf_counter() - t0)
+    achieved = ALG_BYTES_PER_POINT * n / (acc_ms / a.steps * 1e-3) / 1e9
+    return {
+        "metric": "vesta_msm_2e20_per_sec", "value": world * a.steps / float(t.item()), "unit": "MSM/s (n=2^20, Vesta)", "n_gpus": world,
+        "steps": a.steps, "warmup": W, "ms_per_step": float(t.item()) / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u256 modular (8x32 Montgomery)", "data": "synthetic",
+        "config": {"workload": "msm20: BASELINE config 2, one 2^20-point Vesta MSM per step; bases = vesta.srs g[0..65536) extended by the same hash-to-curve rule to 2^20 (K-D), resident as a 13-window fixed-base table (832 MiB); scalars SplitMix64 seed 0x4D494E41",
+                   "l2": "table 832 MiB + 32 MiB scalars > 126 MB L2", "window_bits": 20},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_accumulate", "peak_source": which, "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * n},
+        "cpu_baseline": {"value": cpu, "unit": "MSM/s (n=2^20, Vesta)", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "1 MSM, oracle/pasta_ref.c (arkworks window rule)"},
+        "e2e": {"value": world * a.steps / float(te.item()), "unit": "MSM/s (n=2^20, Vesta)", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 64},
+        "gpu_launches": int(launches), "clocks": sampler.summary(),
+    }
 
 
 def main():
@@ -113,6 +390,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20"])
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
@@ -129,76 +407,15 @@ def main():
     import __graft_entry__ as entry
     import mina_bridge_b200 as mb
 
-    entry.build()
+    if rank == 0:
+        entry.build()  # one builder; the others wait for the finished library / SRS cache
+    if world > 1:
+        dist.barrier()
     mb.init(local)
     dev = torch.device("cuda", local)
-    host = synth_scalars_host(BATCH, 1234 + rank)
-    pinned = torch.frombuffer(bytearray(host), dtype=torch.int32).pin_memory()
-    d_sc = pinned.to(dev, non_blocking=True)
-    d_out = torch.zeros(BATCH * 16, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step(want_ms=False):
-        return mb.msm_srs_device(mb.CURVE_VESTA, BATCH, N_POINTS, d_sc.data_ptr(), d_out.data_ptr(), stream, want_ms)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(a.warmup, 3)):
-        step()
-    sampler = ClockSampler()
-    sampler.start()
-    l0 = mb.launch_count()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    acc_ms = 0.0
-    for _ in range(a.steps):
-        acc_ms += step(True)
-    e1.record()
-    barrier()
-    launches = mb.launch_count() - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-
-    # end to end: host buffers through the C ABI (H2D of scalars + D2H of results inside the call)
-    for _ in range(2):
-        mb.msm_srs(mb.CURVE_VESTA, host, N_POINTS)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        mb.msm_srs(mb.CURVE_VESTA, host, N_POINTS)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    sampler.stop.set()
-    sampler.join()
-
+    line = (bench_state if a.workload == "state1024" else bench_msm20)(a, torch, dist, mb, rank, world, dev)
     if rank == 0:
-        peak, which = peaks()
-        acc_avg_ms = acc_ms / a.steps
-        achieved = ALG_BYTES_PER_POINT * N_POINTS * BATCH / (acc_avg_ms * 1e-3) / 1e9
-        cpu = cpu_sample(os.cpu_count() or 1, 4)
-        print(json.dumps({
-            "metric": METRIC, "value": world * BATCH * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u256 modular (8x32 Montgomery)", "data": "synthetic",
-            "config": {"workload": "per-proof accumulator-check MSM (SURVEY row a7), %d MSMs/step/GPU, n=65536 Vesta over the resident SRS" % BATCH,
-                       "absent_stages": ABSENT, "l2": "scalars 128 MiB/step > 126 MB L2", "window_bits": 16},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_accumulate", "peak_source": which,
-                         "note": "integer-issue-bound by construction (SURVEY 8d); modmul/s = %.3g" % (10 * 16 * N_POINTS * BATCH / (acc_avg_ms * 1e-3))},
-            "cpu_baseline": {"value": cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": "4 MSMs, oracle/pasta_ref.c (arkworks window rule, 1 thread/window); not the reference binary"},
-            "e2e": {"value": world * BATCH * a.steps / float(e2e_s.item()), "unit": UNIT,
-                    "h2d_bytes_per_step": BATCH * N_POINTS * 32, "d2h_bytes_per_step": BATCH * 64},
-            "gpu_launches": int(launches), "clocks": sampler.summary(),
-        }))
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -69,6 +69,13 @@ int mina_b200_msm(int curve, uint32_t n, const uint8_t *scalars32, const uint8_t
  * of the last chunk. */
 int mina_b200_msm_srs_device(int curve, uint32_t nmsm, uint32_t n, const void *d_scalars, void *d_out64,
                              void *cuda_stream, float *accumulate_ms);
+/* Fixed-base MSM over a caller-supplied base set that stays resident (BASELINE config 2: 2^20 Vesta
+ * points): load once (builds the window table: ceil(255/c)+... x n x 64 B), then run any number of MSMs.
+ * Points are validated (canonical, on curve).  window_bits 0 = 16. */
+int mina_b200_fixed_base_load(int curve, uint32_t n, const uint8_t *points64, int window_bits);
+int mina_b200_fixed_base_msm(int curve, uint32_t nmsm, const uint8_t *scalars32, uint8_t *out64);
+int mina_b200_fixed_base_msm_device(int curve, uint32_t nmsm, const void *d_scalars, void *d_out64, void *cuda_stream,
+                                    float *accumulate_ms);
 /* MSM engine tuning (takes effect at the next init / table rebuild): window bits and running-sum
  * chunk.  Returns 0 on success. */
 int mina_b200_msm_configure(int curve, int window_bits, int precompute, int leaf);
@@ -108,6 +115,12 @@ int mina_b200_verify_account_stages(size_t n, const unsigned char *const *proofs
 /* accumulator_check from raw proof bytes: ok3 = {wrap/Vesta, step/Pallas #0, #1}. */
 int mina_b200_accumulator_check(const unsigned char *proof, size_t proof_len, uint8_t ok3[3]);
 int mina_b200_accumulator_check_batch(size_t n, const unsigned char *const *proofs, const size_t *proof_lens, int mode, uint8_t *ok3);
+
+/* Device-resident variant (bench `value` leg): d_pre16 = m*k 16-byte prechallenges and d_pts64 = m
+ * canonical affine points already in HBM (k = 16 on Vesta, 15 on Pallas); ok_host gets m bytes.
+ * kernel_ms (may be NULL): float[2] = summed CUDA-event time of {k_accumulate, k_bpoly_combine}. */
+int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, const void *d_pts64, int mode, uint8_t *ok_host,
+                                  float *kernel_ms);
 
 /* ---- K4 / K2 / K5: IPA scalar helpers (host buffers, canonical 32-byte field elements) -------------- */
 /* ScalarChallenge::to_field for n 16-byte prechallenges landing in `field` (endo = that field's endo_r). */

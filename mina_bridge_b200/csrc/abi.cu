@@ -28,6 +28,7 @@ uint64_t engine_launches() {
     Context &c = ctx();
     for (int k = 0; k < 2; k++) {
         if (c.curve[k].fixed) n += c.curve[k].fixed->launches();
+        if (c.curve[k].user) n += c.curve[k].user->launches();
         if (c.curve[k].var) n += c.curve[k].var->launches();
     }
     return n;
@@ -130,10 +131,18 @@ static void destroy_device_state(Context &c) {
     for (int k = 0; k < 2; k++) {
         c.curve[k].fixed.reset();
         c.curve[k].var.reset();
+        c.curve[k].user.reset();
+        if (c.curve[k].d_user) cudaFree(c.curve[k].d_user);
+        c.curve[k].d_user = nullptr;
+        c.curve[k].user_n = 0;
         if (c.curve[k].d_srs) cudaFree(c.curve[k].d_srs);
         c.curve[k].d_srs = nullptr;
         if (c.d_poseidon_tab[k]) cudaFree(c.d_poseidon_tab[k]);
         c.d_poseidon_tab[k] = nullptr;
+    }
+    for (int i = 0; i < 2; i++) {
+        if (c.ev_combine[i]) cudaEventDestroy(c.ev_combine[i]);
+        c.ev_combine[i] = nullptr;
     }
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
@@ -365,6 +374,100 @@ int mina_b200_msm(int curve, uint32_t n, const uint8_t *scalars32, const uint8_t
     ABI_CATCH
 }
 
+int mina_b200_fixed_base_load(int curve, uint32_t n, const uint8_t *points64, int window_bits) {
+    ABI_TRY
+    require_ready();
+    if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
+    if (n == 0) throw std::runtime_error("fixed_base_load: empty base set");
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    CurveCtx &cc = c.curve[curve];
+    AbiScratch &sc = scratch();
+    cc.user.reset();
+    if (cc.d_user) cudaFree(cc.d_user);
+    cc.d_user = nullptr;
+    cc.user_n = 0;
+    CTX_CUDA_OK(cudaMalloc(&cc.d_user, (size_t)n * sizeof(affine)));
+    uint32_t *d_can = sc.pts_can.reserve((size_t)n * 16);
+    uint8_t *d_bad = sc.bytes.reserve(4);
+    CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_can, points64, (size_t)n * 64, cudaMemcpyHostToDevice, c.stream));
+    launch_affine_to_mont_checked(curve, d_can, cc.d_user, n, (uint32_t *)d_bad, c.stream);
+    c.launches += 1;
+    uint32_t bad = 0;
+    CTX_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    if (bad) throw std::runtime_error("fixed_base_load: a base point is non-canonical or not on the curve");
+    MsmConfig cfg;
+    cfg.precompute = true;
+    cfg.c = window_bits > 0 ? window_bits : 16;
+    cc.user.reset(make_msm_engine(curve));
+    cc.user->set_bases(cc.d_user, n, cfg, c.stream);
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    cc.user_n = n;
+    return 0;
+    ABI_CATCH
+}
+
+int mina_b200_fixed_base_msm_device(int curve, uint32_t nmsm, const void *d_scalars, void *d_out64, void *cuda_stream,
+                                    float *accumulate_ms) {
+    ABI_TRY
+    require_ready();
+    if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    CurveCtx &cc = c.curve[curve];
+    if (!cc.user) throw std::runtime_error("fixed_base_msm: no base set loaded");
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    AbiScratch &sc = scratch();
+    affine *out = sc.out.reserve(std::max<uint32_t>(nmsm, 1));
+    cc.user->enable_kernel_timing(accumulate_ms != nullptr);
+    cc.user->run((const uint32_t *)d_scalars, nmsm, cc.user_n, out, s);
+    launch_affine_from_mont(curve, out, (uint32_t *)d_out64, nmsm, s);
+    c.launches += 1;
+    if (accumulate_ms) {
+        CTX_CUDA_OK(cudaStreamSynchronize(s));
+        *accumulate_ms = cc.user->last_accumulate_ms();
+    }
+    return 0;
+    ABI_CATCH
+}
+
+int mina_b200_fixed_base_msm(int curve, uint32_t nmsm, const uint8_t *scalars32, uint8_t *out64) {
+    ABI_TRY
+    require_ready();
+    if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    CurveCtx &cc = c.curve[curve];
+    if (!cc.user) throw std::runtime_error("fixed_base_msm: no base set loaded");
+    if (nmsm == 0) return 0;
+    AbiScratch &sc = scratch();
+    const size_t per = (size_t)cc.user_n * 8;
+    affine *out = sc.out.reserve(nmsm);
+    uint32_t *can = sc.out_can.reserve((size_t)nmsm * 16);
+    cc.user->enable_kernel_timing(false);
+    for (uint32_t k = 0; k < nmsm; k++) {  // one MSM per chunk, double-buffered like mina_b200_msm_srs
+        int b = k & 1;
+        uint32_t *d_sc = sc.scalars[b].reserve(per);
+        if (k >= 2) CTX_CUDA_OK(cudaStreamWaitEvent(c.copy_stream, sc.consumed[b], 0));
+        CTX_CUDA_OK(cudaMemcpyAsync(d_sc, scalars32 + (size_t)k * per * 4, per * 4, cudaMemcpyHostToDevice, c.copy_stream));
+        CTX_CUDA_OK(cudaEventRecord(sc.copied[b], c.copy_stream));
+        CTX_CUDA_OK(cudaStreamWaitEvent(c.stream, sc.copied[b], 0));
+        cc.user->run(d_sc, 1, cc.user_n, out + k, c.stream);
+        CTX_CUDA_OK(cudaEventRecord(sc.consumed[b], c.stream));
+    }
+    launch_affine_from_mont(curve, out, can, nmsm, c.stream);
+    c.launches += 1;
+    CTX_CUDA_OK(cudaMemcpyAsync(out64, can, (size_t)nmsm * 64, cudaMemcpyDeviceToHost, c.stream));
+    if (cc.user->take_error(c.stream) & 1u) throw std::runtime_error("msm: a scalar is >= 2^255 (not a canonical field element); result discarded");
+    return 0;
+    ABI_CATCH
+}
+
 // ---- K4 / K2 / K5 / K3 hooks: host buffers in, host buffers out, canonical field elements --------------
 int mina_b200_endo_to_field(int field, uint32_t n, const uint8_t *pre16, uint8_t *out32) {
     ABI_TRY
@@ -496,6 +599,10 @@ __global__ void k_field_op(int op, uint32_t n, const fe *a, const fe *b, fe *out
             case 13: r0 = Fd<F>::sub(a[i], b[i]); break;
             case 14: r0 = Fd<F>::add_portable(a[i], b[i]); break;
             case 15: r0 = Fd<F>::sub_portable(a[i], b[i]); break;
+#ifdef __CUDA_ARCH__
+            case 16: r0 = Fd<F>::mul_ptx(a[i], b[i]); break;   // first-generation multiplier
+            case 17: r0 = Fd<F>::mul_ptx2(a[i], b[i]); break;  // IMAD.WIDE-chain reduction (the default)
+#endif
 #ifdef __CUDA_ARCH__
             case 20: case 21: {
                 uint32_t U[16];

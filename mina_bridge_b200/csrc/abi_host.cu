@@ -2,6 +2,7 @@
 // without a GPU, so the CPU test tier can check it against the oracle.
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 #include "../../include/mina_b200.h"
 #include "consensus.hpp"
@@ -37,13 +38,20 @@ int host_field_op_t(int op, uint32_t n, const uint8_t *a32, const uint8_t *b32, 
 template <class B>
 void host_srs_t(uint32_t first, uint32_t count, uint8_t *out64, uint8_t *h64) {
     host::GroupMap<B> gm;
-    for (uint32_t k = 0; k < count; k++) {
-        uint32_t i = first + k;
-        uint8_t msg[4] = {(uint8_t)(i >> 24), (uint8_t)(i >> 16), (uint8_t)(i >> 8), (uint8_t)i};
-        host::Affine<B> p = gm.to_group(host::srs_hash_to_field<B>(msg, 4));
-        p.x.to_bytes_le(out64 + 64 * (size_t)k);
-        p.y.to_bytes_le(out64 + 64 * (size_t)k + 32);
-    }
+    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 64);
+    if (count < 256) nthreads = 1;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; t++)
+        pool.emplace_back([&, t]() {
+            for (uint32_t k = t; k < count; k += nthreads) {
+                uint32_t i = first + k;
+                uint8_t msg[4] = {(uint8_t)(i >> 24), (uint8_t)(i >> 16), (uint8_t)(i >> 8), (uint8_t)i};
+                host::Affine<B> p = gm.to_group(host::srs_hash_to_field<B>(msg, 4));
+                p.x.to_bytes_le(out64 + 64 * (size_t)k);
+                p.y.to_bytes_le(out64 + 64 * (size_t)k + 32);
+            }
+        });
+    for (auto &th : pool) th.join();
     if (h64) {
         const uint8_t misc[12] = {'s', 'r', 's', '_', 'm', 'i', 's', 'c', 0, 0, 0, 0};
         host::Affine<B> p = gm.to_group(host::srs_hash_to_field<B>(misc, 12));

@@ -36,6 +36,9 @@ struct CurveCtx {
     affine *d_srs = nullptr;  // depth + 1 points (last = h), Montgomery
     std::unique_ptr<MsmEngineBase> fixed;  // over the resident SRS
     std::unique_ptr<MsmEngineBase> var;    // caller-supplied bases
+    std::unique_ptr<MsmEngineBase> user;   // caller-supplied bases that stay resident (fixed-base table)
+    affine *d_user = nullptr;
+    uint32_t user_n = 0;
     MsmConfig cfg;
     std::vector<uint8_t> host_canonical;  // (depth + 1) x 64 bytes canonical, for tests / host logic
 };
@@ -112,6 +115,10 @@ struct Context {
     fe *d_poseidon_tab[2] = {nullptr, nullptr};
     std::mutex mu;  // the device lock: one GPU work item (a whole coalesced batch) at a time
     std::atomic<uint64_t> launches{0};
+    bool time_accumulate = false;  // bench hook: sum the CUDA-event time of k_accumulate in per-proof mode
+    float accumulate_ms = 0.f;
+    float combine_ms = 0.f;        // same hook for k_bpoly_combine in RLC mode
+    cudaEvent_t ev_combine[2] = {nullptr, nullptr};
     VerifierState *verifier = nullptr;  // owned; created / released by verifier.cu
 };
 

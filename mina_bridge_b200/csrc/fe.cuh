@@ -14,6 +14,16 @@
 
 namespace pasta {
 
+#ifdef __CUDACC__
+// Values ptxas must not see through.  -p^-1 mod 2^32 is 0xffffffff for both Pasta primes, so the
+// Montgomery quotient digit is just -v; written as `0 - v`, ptxas rewrites m*t as v*(-t) for the low
+// halves only, which splits every lo/hi pair and blocks the IMAD.WIDE fusion mul_ptx2 is built on.
+// Reading the factor from constant memory costs one IMAD instead of one IADD3 and keeps the pairs.
+// The zero is used to order the product before the reduction (see mul_ptx2).
+static __constant__ uint32_t PASTA_NINV32 = 0xffffffffu;
+static __constant__ uint32_t PASTA_ZERO = 0u;
+#endif
+
 struct alignas(16) fe {
     uint32_t v[8];
 };
@@ -320,6 +330,118 @@ struct Fd {
         return cond_sub_p(r);
     }
 
+    // ---- second-generation multiplication: reduction on IMAD.WIDE carry chains -------------------------
+    // The product is left in its two parity accumulators (X: columns with i+j even, Y: odd, stored one
+    // limb down; true value = X + (Y << 32)) and the eight Montgomery rounds add m_i * (t1, t2, t3)
+    // straight into them: m_i*t1 and m_i*t3 land on register pairs of one accumulator, m_i*t2 on a pair
+    // of the other, so every product is ONE IMAD.WIDE.U32(.X) with carry-in/out instead of an IMAD +
+    // IADD3.X + IMAD.HI + IADD3.X quartet.  Only limb i itself is merged per round (to get m_i); carry
+    // bits that fall off a chain are counted in K[limb] and folded back in when that limb is merged.
+    static __device__ __forceinline__ void redc_chain4(uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t &a3, uint32_t &k,
+                                                       uint32_t m) {
+        asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+            "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+            "addc.u32 %4, %4, 0;"
+            : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(k)
+            : "r"(m), "r"(F::MOD(1)), "r"(F::MOD(3)));
+    }
+    static __device__ __forceinline__ void redc_chain2(uint32_t &b0, uint32_t &b1, uint32_t &k, uint32_t m) {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, %2, 0;"
+            : "+r"(b0), "+r"(b1), "+r"(k)
+            : "r"(m), "r"(F::MOD(2)));
+    }
+    static __device__ __forceinline__ fe mul_ptx2(const fe &a, const fe &b) {
+        uint32_t X[17], Y[17];
+#pragma unroll
+        for (int i = 8; i < 17; i++) X[i] = Y[i] = 0;
+        mul_row(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+        mul_row(Y, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            if (i & 1) {
+                mad_row(&Y[i - 1], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+                mad_row(&X[i + 1], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+            } else {
+                mad_row(&X[i], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+                mad_row(&Y[i], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+            }
+        }
+        // Ordering only: without this data dependency ptxas interleaves the reduction rounds with the
+        // product rows, keeps a dozen carry chains alive at once and spills predicates (35 P2R + 43 ISETP
+        // per multiplication measured); with it at most three chains are live.
+        X[0] += (X[16] | Y[14]) & PASTA_ZERO;
+        uint32_t K[13], m[8], c = 0, d7 = 0;
+#pragma unroll
+        for (int i = 0; i < 13; i++) K[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i == 7) {
+                // the 2^254 part of p: (m0 << 30) belongs to limb 7 and must be there before it is merged;
+                // carry by comparison (ptxas 12.9 mis-fuses neg + shl + add.cc into LEA, see redc())
+                uint32_t s30 = m[0] << 30;
+                X[7] += s30;
+                d7 = X[7] < s30 ? 1u : 0u;
+            }
+            uint64_t sum = (uint64_t)X[i] + (uint64_t)(i ? Y[i - 1] : 0u) + (uint64_t)(c + K[i]);
+            uint32_t v = (uint32_t)sum, scratch;
+            m[i] = v * PASTA_NINV32;  // = -v
+            // limb i becomes v + m_i = 0 or 2^32: the carry of that addition is (v != 0)
+            asm("add.cc.u32 %0, %2, %3;\n\t"
+                "addc.u32 %1, %4, 0;"
+                : "=&r"(scratch), "=r"(c)
+                : "r"(v), "r"(m[i]), "r"((uint32_t)(sum >> 32)));
+            if (i & 1) {
+                redc_chain4(X[i + 1], X[i + 2], X[i + 3], X[i + 4], K[i + 5], m[i]);  // true limbs i+1 .. i+4
+                redc_chain2(Y[i + 1], Y[i + 2], K[i + 4], m[i]);                      // true limbs i+2, i+3
+            } else {
+                redc_chain4(Y[i], Y[i + 1], Y[i + 2], Y[i + 3], K[i + 5], m[i]);
+                redc_chain2(X[i + 2], X[i + 3], K[i + 4], m[i]);
+            }
+        }
+        // true limbs 8..15 = X[8..16) + Y[7..15) + (m >> 2 funnel) + pending carries
+        uint32_t sh[8];
+#pragma unroll
+        for (int k = 0; k < 7; k++) sh[k] = __funnelshift_r(m[k], m[k + 1], 2);
+        sh[7] = m[7] >> 2;
+        uint32_t k8 = c + d7 + K[8];
+        uint32_t r[8];
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+            : "r"(X[8]), "r"(X[9]), "r"(X[10]), "r"(X[11]), "r"(X[12]), "r"(X[13]), "r"(X[14]), "r"(X[15]),
+              "r"(Y[7]), "r"(Y[8]), "r"(Y[9]), "r"(Y[10]), "r"(Y[11]), "r"(Y[12]), "r"(Y[13]), "r"(Y[14]));
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;\n\t"
+            "add.cc.u32 %0, %0, %16;\n\t"
+            "addc.cc.u32 %1, %1, %17;\n\t"
+            "addc.cc.u32 %2, %2, %18;\n\t"
+            "addc.cc.u32 %3, %3, %19;\n\t"
+            "addc.cc.u32 %4, %4, %20;\n\t"
+            "addc.cc.u32 %5, %5, 0;\n\t"
+            "addc.cc.u32 %6, %6, 0;\n\t"
+            "addc.u32 %7, %7, 0;"
+            : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+            : "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]), "r"(sh[4]), "r"(sh[5]), "r"(sh[6]), "r"(sh[7]),
+              "r"(k8), "r"(K[9]), "r"(K[10]), "r"(K[11]), "r"(K[12]));
+        return cond_sub_p(r);
+    }
+
     static __device__ __forceinline__ fe add_ptx(const fe &a, const fe &b) {
         uint32_t r[8];
         asm("add.cc.u32 %0, %8, %16;\n\t"
@@ -371,7 +493,7 @@ struct Fd {
 
     PASTA_HD static fe mul(const fe &a, const fe &b) {
 #ifdef __CUDA_ARCH__
-        return mul_ptx(a, b);
+        return mul_ptx2(a, b);
 #else
         return mul_portable(a, b);
 #endif

@@ -214,7 +214,21 @@ static __global__ void __launch_bounds__(256) k_scan_finish(uint32_t *__restrict
 // One thread per bucket; the bucket's points are a contiguous run of `pairs`.  Each step gathers one
 // 64-byte affine point (4 x LDG.128, mostly L2 hits: the whole table is 64 MiB) and does one mixed
 // XYZZ addition (10 field multiplications).  The next point is fetched before the current addition
-// so the gather latency hides behind ~1.3k integer instructions.
+// so the gather latency hides behind ~2.5k integer instructions.
+//
+// Round-2 changes, each backed by profiles/r2_k_accumulate_{before,after}.md:
+//   * buckets are visited in order of decreasing population (counting sort of the bucket sizes,
+//     k_order_*): with one bucket per thread and Poisson(32) populations a warp used to wait for its
+//     longest lane (22.8 of 32 lanes active on average); sorted, all 32 lanes of a warp have
+//     (nearly) the same trip count;
+//   * the field multiplication is a real call (`mul_call`) instead of ten inlined copies: the loop
+//     body shrinks from ~85 KB to ~12 KB of SASS and stops missing the instruction cache (the top
+//     stall reason before was `no_instruction`);
+//   * a bucket contributes at most ACC_SEG points here; the rest of an over-full bucket (adversarial
+//     scalars: all-equal digits put up to n*W points in ONE bucket) is summed by a whole block in
+//     k_accumulate_overflow, so no thread ever walks more than ACC_SEG points.
+static constexpr uint32_t ACC_SEG = 256;
+
 template <class F>
 __device__ __forceinline__ affine load_point(const affine *__restrict__ table, uint32_t entry) {
     const uint4 *p = reinterpret_cast<const uint4 *>(table + (entry & 0x7fffffffu));
@@ -228,12 +242,105 @@ __device__ __forceinline__ affine load_point(const affine *__restrict__ table, u
 }
 
 template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ pairs,
-                                                    const affine *__restrict__ table, xyzz *__restrict__ buckets,
-                                                    uint32_t nbuckets) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbuckets) return;
+__device__ __noinline__ fe mul_call(const fe a, const fe b) {
+    return Fd<F>::mul(a, b);
+}
+// Ec<F>::add_mixed with the multiplications out of line (same formulas, "madd-2008-s")
+template <class F>
+__device__ __forceinline__ void add_mixed_compact(xyzz &p, const affine &q) {
+    using fd = Fd<F>;
+    if (Ec<F>::is_identity(q)) return;
+    if (Ec<F>::is_identity(p)) {
+        p = Ec<F>::from_affine(q);
+        return;
+    }
+    fe U2 = mul_call<F>(q.x, p.zz);
+    fe S2 = mul_call<F>(q.y, p.zzz);
+    fe P = fd::sub(U2, p.x);
+    fe R = fd::sub(S2, p.y);
+    if (fe_is_zero(P)) {
+        if (fe_is_zero(R))
+            p = Ec<F>::dbl_affine(q);
+        else
+            p = Ec<F>::identity();
+        return;
+    }
+    fe PP = mul_call<F>(P, P);
+    fe PPP = mul_call<F>(P, PP);
+    fe Q = mul_call<F>(p.x, PP);
+    fe X3 = fd::sub(fd::sub(mul_call<F>(R, R), PPP), fd::dbl(Q));
+    fe Y3 = fd::sub(mul_call<F>(R, fd::sub(Q, X3)), mul_call<F>(p.y, PPP));
+    p.x = X3;
+    p.y = Y3;
+    p.zz = mul_call<F>(p.zz, PP);
+    p.zzz = mul_call<F>(p.zzz, PPP);
+}
+
+// -- bucket visiting order: counting sort of min(population, ACC_SEG), longest first -------------------
+static constexpr int ORDER_BINS = ACC_SEG + 1;
+static constexpr int ORDER_BLOCK = 1024;
+// pass 1: histogram of bucket sizes (per-block shared histogram, one global atomic per non-empty bin),
+// plus the list of over-full buckets
+static __global__ void __launch_bounds__(ORDER_BLOCK) k_order_hist(const uint32_t *__restrict__ offsets, uint32_t nb,
+                                                            uint32_t *__restrict__ hist, uint32_t *__restrict__ over_list,
+                                                            uint32_t *__restrict__ over_count) {
+    __shared__ uint32_t sh[ORDER_BINS];
+    for (int i = threadIdx.x; i < ORDER_BINS; i += ORDER_BLOCK) sh[i] = 0;
+    __syncthreads();
+    uint32_t b = blockIdx.x * ORDER_BLOCK + threadIdx.x;
+    if (b < nb) {
+        uint32_t cnt = offsets[b + 1] - offsets[b];
+        if (cnt > ACC_SEG) {
+            over_list[atomicAdd(over_count, 1u)] = b;
+            cnt = ACC_SEG;
+        }
+        atomicAdd(&sh[cnt], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ORDER_BINS; i += ORDER_BLOCK)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// pass 2 (one block): start[c] = number of buckets with a larger size (descending order)
+static __global__ void __launch_bounds__(32) k_order_scan(uint32_t *__restrict__ hist) {
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int c = ORDER_BINS - 1; c >= 0; c--) {
+            uint32_t h = hist[c];
+            hist[c] = run;
+            run += h;
+        }
+    }
+}
+// pass 3: scatter bucket ids; a block reserves a range per bin with one global atomic
+static __global__ void __launch_bounds__(ORDER_BLOCK) k_order_scatter(const uint32_t *__restrict__ offsets, uint32_t nb,
+                                                               uint32_t *__restrict__ cursors, uint32_t *__restrict__ order) {
+    __shared__ uint32_t sh[ORDER_BINS];
+    __shared__ uint32_t base[ORDER_BINS];
+    for (int i = threadIdx.x; i < ORDER_BINS; i += ORDER_BLOCK) sh[i] = 0;
+    __syncthreads();
+    uint32_t b = blockIdx.x * ORDER_BLOCK + threadIdx.x;
+    uint32_t cnt = 0, local = 0;
+    if (b < nb) {
+        cnt = offsets[b + 1] - offsets[b];
+        cnt = cnt > ACC_SEG ? ACC_SEG : cnt;
+        local = atomicAdd(&sh[cnt], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ORDER_BINS; i += ORDER_BLOCK)
+        if (sh[i]) base[i] = atomicAdd(&cursors[i], sh[i]);
+    __syncthreads();
+    if (b < nb) order[base[cnt] + local] = b;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128, 4) k_accumulate(const uint32_t *__restrict__ order, const uint32_t *__restrict__ offsets,
+                                                       const uint32_t *__restrict__ pairs, const affine *__restrict__ table,
+                                                       xyzz *__restrict__ buckets, uint32_t nbuckets) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbuckets) return;
+    uint32_t b = order[t];
     uint32_t k = offsets[b], end = offsets[b + 1];
+    if (end - k > ACC_SEG) end = k + ACC_SEG;
     xyzz acc = Ec<F>::identity();
     if (k < end) {
         uint32_t e = pairs[k];
@@ -247,7 +354,7 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t *__restrict__
                 q_next = load_point<F>(table, e_next);
             }
             if (e >> 31) q.y = Fd<F>::neg(q.y);
-            Ec<F>::add_mixed(acc, q);
+            add_mixed_compact<F>(acc, q);
             if (!more) break;
             q = q_next;
             e = e_next;
@@ -255,6 +362,55 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t *__restrict__
         }
     }
     buckets[b] = acc;
+}
+
+template <class F>
+__device__ __forceinline__ xyzz shfl_down_point(const xyzz &p, int delta);
+
+// Over-full buckets: one block per listed bucket (block-stride), threads stride over the points past
+// ACC_SEG, then a shuffle / shared-memory tree; the block's sum is added into the bucket.
+static constexpr int OVER_THREADS = 256;
+template <class F>
+__global__ void __launch_bounds__(OVER_THREADS) k_accumulate_overflow(const uint32_t *__restrict__ over_list,
+                                                                      const uint32_t *__restrict__ over_count,
+                                                                      const uint32_t *__restrict__ offsets,
+                                                                      const uint32_t *__restrict__ pairs, const affine *__restrict__ table,
+                                                                      xyzz *__restrict__ buckets) {
+    __shared__ xyzz warp_part[OVER_THREADS / 32];
+    const uint32_t nover = *over_count;
+    for (uint32_t it = blockIdx.x; it < nover; it += gridDim.x) {
+        const uint32_t b = over_list[it];
+        const uint32_t begin = offsets[b] + ACC_SEG, end = offsets[b + 1];
+        xyzz acc = Ec<F>::identity();
+        for (uint32_t k = begin + threadIdx.x; k < end; k += OVER_THREADS) {
+            uint32_t e = pairs[k];
+            affine q = load_point<F>(table, e);
+            if (e >> 31) q.y = Fd<F>::neg(q.y);
+            add_mixed_compact<F>(acc, q);
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            xyzz o = shfl_down_point<F>(acc, d);
+            Ec<F>::add(acc, o);
+        }
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) warp_part[wid] = acc;
+        __syncthreads();
+        if (wid == 0) {
+            acc = lane < OVER_THREADS / 32 ? warp_part[lane] : Ec<F>::identity();
+#pragma unroll 1
+            for (int d = 4; d >= 1; d >>= 1) {
+                xyzz o = shfl_down_point<F>(acc, d);
+                Ec<F>::add(acc, o);
+            }
+            if (lane == 0) {
+                xyzz cur = buckets[b];
+                Ec<F>::add(cur, acc);
+                buckets[b] = cur;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // ---- running-sum reduction -------------------------------------------------------------------------
@@ -547,6 +703,9 @@ class MsmEngine : public MsmEngineBase {
         free_dev(offsets_);
         free_dev(tile_sums_);
         free_dev(pairs_);
+        free_dev(order_);
+        free_dev(over_list_);
+        free_dev(order_hist_);
         free_dev(buckets_);
         free_dev(lvlS_[0]);
         free_dev(lvlS_[1]);
@@ -612,6 +771,9 @@ class MsmEngine : public MsmEngineBase {
         alloc(offsets_, (want_b + 1) * sizeof(uint32_t));
         alloc(tile_sums_, (ntiles + 1) * sizeof(uint32_t));
         alloc(pairs_, std::max<uint64_t>(want_p, 1) * sizeof(uint32_t));
+        alloc(order_, want_b * sizeof(uint32_t));
+        alloc(over_list_, (want_p / ACC_SEG + 1) * sizeof(uint32_t));
+        alloc(order_hist_, (ORDER_BINS + 1) * sizeof(uint32_t));
         alloc(buckets_, want_b * sizeof(xyzz));
         alloc(lvlS_[0], first * sizeof(xyzz));
         alloc(lvlS_[1], first * sizeof(xyzz));
@@ -658,10 +820,18 @@ class MsmEngine : public MsmEngineBase {
         k_scan_finish<<<(nb + 1 + 255) / 256, 256, 0, s>>>(offsets_, counters_, tile_sums_, nb, ntiles);
         launches_ += 3;
         launch_digits<true>(src, d_src, dp, dblocks, counters_, pairs_, s);
+        // visiting order (longest bucket first) and the list of over-full buckets
+        CUDA_OK(cudaMemsetAsync(order_hist_, 0, (ORDER_BINS + 1) * sizeof(uint32_t), s));
+        k_order_hist<<<(nb + ORDER_BLOCK - 1) / ORDER_BLOCK, ORDER_BLOCK, 0, s>>>(offsets_, nb, order_hist_, over_list_, order_hist_ + ORDER_BINS);
+        k_order_scan<<<1, 32, 0, s>>>(order_hist_);
+        k_order_scatter<<<(nb + ORDER_BLOCK - 1) / ORDER_BLOCK, ORDER_BLOCK, 0, s>>>(offsets_, nb, order_hist_, order_);
+        launches_ += 3;
         if (timing_) CUDA_OK(cudaEventRecord(ev0_, s));
-        k_accumulate<F><<<(nb + 127) / 128, 128, 0, s>>>(offsets_, pairs_, table_, buckets_, nb);
+        k_accumulate<F><<<(nb + 127) / 128, 128, 0, s>>>(order_, offsets_, pairs_, table_, buckets_, nb);
         launches_++;
         if (timing_) CUDA_OK(cudaEventRecord(ev1_, s));
+        k_accumulate_overflow<F><<<296, OVER_THREADS, 0, s>>>(over_list_, order_hist_ + ORDER_BINS, offsets_, pairs_, table_, buckets_);
+        launches_++;
 
         // running-sum levels
         const xyzz *in = buckets_;
@@ -697,6 +867,7 @@ class MsmEngine : public MsmEngineBase {
     const affine *table_ = nullptr;
     affine *table_own_ = nullptr;
     uint32_t *counters_ = nullptr, *offsets_ = nullptr, *tile_sums_ = nullptr, *pairs_ = nullptr, *err_ = nullptr;
+    uint32_t *order_ = nullptr, *over_list_ = nullptr, *order_hist_ = nullptr;
     xyzz *buckets_ = nullptr, *lvlS_[2] = {nullptr, nullptr}, *lvlW_ = nullptr, *sumW_ = nullptr;
     uint64_t cap_buckets_ = 0, cap_pairs_ = 0;
     uint32_t cap_groups_ = 0;

@@ -99,84 +99,123 @@ struct AccumulatorBatch {
     int curve;       // 0 Pallas / 1 Vesta
     int k;           // 15 / 16
     uint32_t m = 0;
-    std::vector<uint8_t> pre;   // m * k * 16
+    std::vector<uint8_t> pre;   // m * k * 16   (host input) ...
     std::vector<uint8_t> pts;   // m * 64
+    const uint8_t *d_pre_ext = nullptr;  // ... or the same two arrays already resident in HBM
+    const uint8_t *d_pts_ext = nullptr;
     std::vector<uint8_t> ok;    // m
 };
 
-static void acc_prepare(Context &c, SideBuffers &sb, const AccumulatorBatch &ab) {
+static __global__ void __launch_bounds__(256) k_points_equal(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint32_t m,
+                                                             uint8_t *__restrict__ ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint4 x = a[4 * (size_t)i + k], y = b[4 * (size_t)i + k];
+        diff |= (x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w);
+    }
+    ok[i] = diff == 0;
+}
+
+struct AccDevice {  // device views of one prepared batch
+    const uint8_t *d_pre = nullptr;
+    const uint32_t *d_pts_can = nullptr;
+};
+
+static AccDevice acc_prepare(Context &c, SideBuffers &sb, const AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;  // scalar field of the curve
     const size_t npre = (size_t)ab.m * ab.k;
-    uint8_t *h_pre = sb.h_pre.reserve(npre * 16);
-    std::memcpy(h_pre, ab.pre.data(), npre * 16);
-    uint8_t *d_pre = sb.d_pre.reserve(npre * 16);
+    AccDevice dv;
+    if (ab.d_pre_ext) {
+        dv.d_pre = ab.d_pre_ext;
+        dv.d_pts_can = reinterpret_cast<const uint32_t *>(ab.d_pts_ext);
+    } else {
+        uint8_t *h_pre = sb.h_pre.reserve(npre * 16 + (size_t)ab.m * 64);
+        std::memcpy(h_pre, ab.pre.data(), npre * 16);
+        std::memcpy(h_pre + npre * 16, ab.pts.data(), (size_t)ab.m * 64);
+        uint8_t *d_pre = sb.d_pre.reserve(npre * 16 + (size_t)ab.m * 64);
+        CTX_CUDA_OK(cudaMemcpyAsync(d_pre, h_pre, npre * 16 + (size_t)ab.m * 64, cudaMemcpyHostToDevice, c.stream));
+        dv.d_pre = d_pre;
+        dv.d_pts_can = reinterpret_cast<const uint32_t *>(d_pre + npre * 16);
+    }
     fe *d_chal = sb.d_chal.reserve(npre);
-    CTX_CUDA_OK(cudaMemcpyAsync(d_pre, h_pre, npre * 16, cudaMemcpyHostToDevice, c.stream));
-    launch_endo_to_field(field, d_pre, d_chal, (uint32_t)npre, c.stream);
+    launch_endo_to_field(field, dv.d_pre, d_chal, (uint32_t)npre, c.stream);
     c.launches += 1;
+    return dv;
 }
 
 static void acc_per_proof(Context &c, SideBuffers &sb, AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
-    acc_prepare(c, sb, ab);
+    AccDevice dv = acc_prepare(c, sb, ab);
     fe *d_tab = sb.d_tab.reserve((size_t)ab.m * BPOLY_TABLE);
     affine *d_res = sb.d_res.reserve(ab.m);
     uint32_t *d_can = sb.d_out_can.reserve((size_t)ab.m * 16);
-    uint8_t *h_out = sb.h_out.reserve((size_t)ab.m * 64);
+    uint8_t *d_ok = reinterpret_cast<uint8_t *>(sb.d_subset.reserve((ab.m + 3) / 4));
+    uint8_t *h_out = sb.h_out.reserve(ab.m);
     launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, nullptr, true, c.stream);
-    cc.fixed->enable_kernel_timing(false);
+    cc.fixed->enable_kernel_timing(c.time_accumulate);
     cc.fixed->run_bpoly(d_tab, ab.m, ab.k, d_res, c.stream);
     launch_affine_from_mont(ab.curve, d_res, d_can, ab.m, c.stream);
-    c.launches += 2;
-    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_can, (size_t)ab.m * 64, cudaMemcpyDeviceToHost, c.stream));
+    k_points_equal<<<(ab.m + 255) / 256, 256, 0, c.stream>>>(reinterpret_cast<const uint4 *>(d_can),
+                                                              reinterpret_cast<const uint4 *>(dv.d_pts_can), ab.m, d_ok);
+    c.launches += 3;
+    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_ok, ab.m, cudaMemcpyDeviceToHost, c.stream));
     if (cc.fixed->take_error(c.stream)) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
-    for (uint32_t i = 0; i < ab.m; i++) ab.ok[i] = std::memcmp(h_out + 64 * (size_t)i, &ab.pts[64 * (size_t)i], 64) == 0;
+    if (c.time_accumulate) c.accumulate_ms += cc.fixed->last_accumulate_ms();
+    for (uint32_t i = 0; i < ab.m; i++) ab.ok[i] = h_out[i];
 }
 
 // One random-linear-combination check over `subset` (indices into the batch).  Returns true iff
 //   < sum_j r_j b_poly_coefficients(chals_j), G > == sum_j r_j C_j.
+// The commitment side runs over ALL m points with r_j masked to zero outside the subset, so the bases
+// are converted and handed to the engine once per batch.
 static bool acc_rlc_check(Context &c, SideBuffers &sb, const AccumulatorBatch &ab, const std::vector<uint32_t> &subset) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
     const uint32_t ns = (uint32_t)subset.size();
     uint32_t *h_sub = sb.h_subset.reserve(ns);
-    uint8_t *h_pts = sb.h_pts.reserve((size_t)ns * 64 + (size_t)ns * 32);
-    uint8_t *h_sc = h_pts + (size_t)ns * 64;
+    uint8_t *h_sc = sb.h_pts.reserve((size_t)ab.m * 32);
+    std::memset(h_sc, 0, (size_t)ab.m * 32);
     for (uint32_t i = 0; i < ns; i++) {
         h_sub[i] = subset[i];
-        std::memcpy(h_pts + 64 * (size_t)i, &ab.pts[64 * (size_t)subset[i]], 64);
-        std::memcpy(h_sc + 32 * (size_t)i, sb.h_r.p + 32 * (size_t)subset[i], 32);
+        std::memcpy(h_sc + 32 * (size_t)subset[i], sb.h_r.p + 32 * (size_t)subset[i], 32);
     }
     uint32_t *d_sub = sb.d_subset.reserve(ns);
-    uint32_t *d_pts_can = sb.d_pts_can.reserve((size_t)ns * 16);
-    uint32_t *d_sc = sb.d_sc.reserve((size_t)ns * 8);
-    affine *d_pts = sb.d_pts.reserve(ns);
-    affine *d_res = sb.d_res.reserve(std::max<uint32_t>(ab.m, 2));
-    uint32_t *d_can = sb.d_out_can.reserve(std::max<size_t>((size_t)ab.m * 16, 32));
-    uint32_t *d_bad = sb.d_bad.reserve(1);
+    uint32_t *d_sc = sb.d_sc.reserve((size_t)ab.m * 8);
+    affine *d_res = sb.d_res.reserve(2);
+    uint32_t *d_can = sb.d_out_can.reserve(32);
     fe *d_S = sb.d_S.reserve((size_t)1 << ab.k);
-    uint8_t *h_out = sb.h_out.reserve(std::max<size_t>((size_t)ab.m * 64, 128));
+    uint8_t *h_out = sb.h_out.reserve(128);
     CTX_CUDA_OK(cudaMemcpyAsync(d_sub, h_sub, (size_t)ns * 4, cudaMemcpyHostToDevice, c.stream));
-    CTX_CUDA_OK(cudaMemcpyAsync(d_pts_can, h_pts, (size_t)ns * 64, cudaMemcpyHostToDevice, c.stream));
-    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, h_sc, (size_t)ns * 32, cudaMemcpyHostToDevice, c.stream));
-    CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, h_sc, (size_t)ab.m * 32, cudaMemcpyHostToDevice, c.stream));
     // g side: S = sum_j r_j s_j, then one MSM over the resident SRS
+    if (c.time_accumulate) {
+        if (!c.ev_combine[0]) {
+            CTX_CUDA_OK(cudaEventCreate(&c.ev_combine[0]));
+            CTX_CUDA_OK(cudaEventCreate(&c.ev_combine[1]));
+        }
+        CTX_CUDA_OK(cudaEventRecord(c.ev_combine[0], c.stream));
+    }
     launch_bpoly_combine(field, sb.d_tab.p, d_sub, ns, ab.k, d_S, c.stream);
-    cc.fixed->enable_kernel_timing(false);
+    if (c.time_accumulate) CTX_CUDA_OK(cudaEventRecord(c.ev_combine[1], c.stream));
+    cc.fixed->enable_kernel_timing(c.time_accumulate);
     cc.fixed->run(reinterpret_cast<const uint32_t *>(d_S), 1, 1u << ab.k, d_res, c.stream);
-    // commitment side: sum_j r_j C_j over caller-supplied bases
-    launch_affine_to_mont_checked(ab.curve, d_pts_can, d_pts, ns, d_bad, c.stream);
-    MsmConfig cfg;
-    cfg.precompute = false;
-    cfg.c = 8;
-    cc.var->set_bases(d_pts, ns, cfg, c.stream);
-    cc.var->run(d_sc, 1, ns, d_res + 1, c.stream);
+    // commitment side: sum_j r_j C_j over the batch's own points
+    cc.var->run(d_sc, 1, ab.m, d_res + 1, c.stream);
     launch_affine_from_mont(ab.curve, d_res, d_can, 2, c.stream);
-    c.launches += 3;
+    c.launches += 2;
     CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_can, 128, cudaMemcpyDeviceToHost, c.stream));
     uint32_t e = cc.fixed->take_error(c.stream) | cc.var->take_error(c.stream);  // synchronises
     if (e) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
+    if (c.time_accumulate) {
+        float ms = 0.f;
+        CTX_CUDA_OK(cudaEventElapsedTime(&ms, c.ev_combine[0], c.ev_combine[1]));
+        c.combine_ms += ms;
+        c.accumulate_ms += cc.fixed->last_accumulate_ms();
+    }
     return std::memcmp(h_out, h_out + 64, 64) == 0;
 }
 
@@ -202,15 +241,28 @@ static void acc_bisect(Context &c, SideBuffers &sb, AccumulatorBatch &ab, const 
 
 static void acc_rlc(Context &c, SideBuffers &sb, AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;
-    acc_prepare(c, sb, ab);
+    CurveCtx &cc = c.curve[ab.curve];
+    AccDevice dv = acc_prepare(c, sb, ab);
     uint8_t *h_r = sb.h_r.reserve((size_t)ab.m * 32);
     for (uint32_t i = 0; i < ab.m; i++) random_128(h_r + 32 * (size_t)i);
     fe *d_r_can = sb.d_r_can.reserve(ab.m), *d_r = sb.d_r.reserve(ab.m);
     fe *d_tab = sb.d_tab.reserve((size_t)ab.m * BPOLY_TABLE);
+    affine *d_pts = sb.d_pts.reserve(ab.m);
+    uint32_t *d_bad = sb.d_bad.reserve(1);
     CTX_CUDA_OK(cudaMemcpyAsync(d_r_can, h_r, (size_t)ab.m * 32, cudaMemcpyHostToDevice, c.stream));
+    CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, c.stream));
     launch_fe_to_mont(field, d_r_can, d_r, ab.m, c.stream);
     launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, d_r, false, c.stream);
-    c.launches += 2;
+    launch_affine_to_mont_checked(ab.curve, dv.d_pts_can, d_pts, ab.m, d_bad, c.stream);
+    c.launches += 3;
+    MsmConfig cfg;
+    cfg.precompute = false;
+    cfg.c = 8;
+    cc.var->set_bases(d_pts, ab.m, cfg, c.stream);
+    uint32_t bad = 0;
+    CTX_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    if (bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
     std::vector<uint32_t> all(ab.m);
     for (uint32_t i = 0; i < ab.m; i++) all[i] = i;
     acc_bisect(c, sb, ab, all, false);
@@ -681,6 +733,47 @@ int mina_b200_accumulator_check_batch(size_t n, const unsigned char *const *proo
         }
         for (size_t t = 0; t < wrap_owner.size(); t++) ok3[3 * wrap_owner[t]] = wrap.ok[t];
         for (size_t t = 0; t < step_owner.size(); t++) ok3[step_owner[t]] = step.ok[t];
+        return 0;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+    } catch (...) {
+        set_error("unknown error");
+    }
+    return -1;
+}
+
+// The same device pipeline over inputs that already sit in HBM (bench `value` leg): d_pre16 = m*k
+// 16-byte prechallenges, d_pts64 = m canonical affine points (validated by the caller), k = 16 for
+// Vesta (curve 1) and 15 for Pallas (curve 0).  ok_host receives m bytes.  The call synchronises.
+int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, const void *d_pts64, int mode, uint8_t *ok_host,
+                                  float *kernel_ms) {
+    try {
+        require_ready();
+        if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
+        AccumulatorBatch ab;
+        ab.curve = curve;
+        ab.k = curve == 1 ? 16 : 15;
+        ab.m = m;
+        ab.d_pre_ext = (const uint8_t *)d_pre16;
+        ab.d_pts_ext = (const uint8_t *)d_pts64;
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        CTX_CUDA_OK(cudaSetDevice(c.device));
+        c.time_accumulate = kernel_ms != nullptr;
+        c.accumulate_ms = 0.f;
+        c.combine_ms = 0.f;
+        try {
+            run_accumulators(c, ab, mode);
+        } catch (...) {
+            c.time_accumulate = false;
+            throw;
+        }
+        c.time_accumulate = false;
+        if (kernel_ms) {
+            kernel_ms[0] = c.accumulate_ms;
+            kernel_ms[1] = c.combine_ms;
+        }
+        if (m) std::memcpy(ok_host, ab.ok.data(), m);
         return 0;
     } catch (const std::exception &e) {
         set_error(e.what());

@@ -366,3 +366,30 @@ def host_poseidon_permute(field: int, table: bytes, states: bytes) -> bytes:
     if rc != 0:
         raise MinaB200Error("host_poseidon_permute failed: %d" % rc)
     return buf.raw[: 96 * n]
+
+
+# ---- device-resident accumulator batches and the resident user base set (bench legs, config 2) ------------
+def accumulators_device(curve: int, m: int, d_pre: int, d_pts: int, mode: int = MODE_RLC, want_ms: bool = False):
+    ok = ctypes.create_string_buffer(max(m, 1))
+    ms = (ctypes.c_float * 2)()
+    _check(load().mina_b200_accumulators_device(curve, ctypes.c_uint32(m), ctypes.c_void_p(d_pre), ctypes.c_void_p(d_pts), mode, ok,
+                                                ms if want_ms else None))
+    return (ok.raw[:m], (ms[0], ms[1])) if want_ms else ok.raw[:m]
+
+
+def fixed_base_load(curve: int, points: bytes, window_bits: int = 0):
+    _check(load().mina_b200_fixed_base_load(curve, ctypes.c_uint32(len(points) // 64), points, window_bits))
+
+
+def fixed_base_msm(curve: int, scalars: bytes, n: int) -> list[bytes]:
+    nmsm = len(scalars) // (32 * n)
+    out = ctypes.create_string_buffer(64 * max(nmsm, 1))
+    _check(load().mina_b200_fixed_base_msm(curve, ctypes.c_uint32(nmsm), scalars, out))
+    return [out.raw[64 * i : 64 * i + 64] for i in range(nmsm)]
+
+
+def fixed_base_msm_device(curve: int, nmsm: int, d_scalars: int, d_out: int, stream: int, want_ms: bool = False):
+    ms = ctypes.c_float(0.0)
+    _check(load().mina_b200_fixed_base_msm_device(curve, ctypes.c_uint32(nmsm), ctypes.c_void_p(d_scalars), ctypes.c_void_p(d_out),
+                                                  ctypes.c_void_p(stream), ctypes.byref(ms) if want_ms else None))
+    return ms.value if want_ms else None

@@ -33,6 +33,29 @@ def test_device_field_ops(gpu):
         assert gpu.field_op(fid, 3, A[: 32 * 64]) == cref.ints_to_bytes([pow(x, -1, m) for x in a[:64]])
 
 
+def test_both_device_multipliers_match_the_portable_product(gpu):
+    """raw Montgomery products (no conversion): op 11 = portable CIOS, 16 = mul_ptx, 17 = mul_ptx2."""
+    rng = random.Random(2)
+    pats = [0, 1, 0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 0xFFFFFFFE]
+    for fid, m in ((0, pasta.P), (1, pasta.Q)):
+        vals = [rng.randrange(m) for _ in range(3000)]
+        # structured limbs: zero / all-ones limbs exercise the (v == 0) carry and the deferred-carry paths
+        for _ in range(3000):
+            v = 0
+            for k in range(8):
+                v |= (rng.choice(pats) if rng.random() < 0.7 else rng.getrandbits(32)) << (32 * k)
+            vals.append(v % m)
+        vals += [0, 1, m - 1, m - 2, (1 << 254) % m, (1 << 255) % m, 2**32 - 1, 2**64 - 1, 2**224]
+        a, b = vals, vals[::-1]
+        A, B = cref.ints_to_bytes(a), cref.ints_to_bytes(b)
+        want = gpu.field_op(fid, 11, A, B)
+        rinv = pow(1 << 256, -1, m)
+        assert want == cref.ints_to_bytes([x * y * rinv % m for x, y in zip(a, b)])
+        assert gpu.field_op(fid, 16, A, B) == want
+        assert gpu.field_op(fid, 17, A, B) == want
+        assert gpu.field_op(fid, 10, A, B) == want
+
+
 def test_device_srs_is_the_reference_srs(gpu):
     pins = json.load(open(os.path.join(GOLDEN, "srs_sha256.json")))
     g, h = gpu.srs_points(1, 0, 65536, True)
