@@ -200,6 +200,7 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
     def step_device(mode, timing=False):
         a1 = mb.accumulators_device(mb.CURVE_VESTA, m, d_pre_w.data_ptr(), d_pts_w.data_ptr(), mode, timing)
         a2 = mb.accumulators_device(mb.CURVE_PALLAS, 2 * m, d_pre_s.data_ptr(), d_pts_s.data_ptr(), mode, timing)
+        # returns (ok bytes, KernelStats) per curve when timing
         ok_w, ok_s = (a1[0], a2[0]) if timing else (a1, a2)
         bits = bytes(ok_w[i] & ok_s[2 * i] & ok_s[2 * i + 1] for i in range(m))
         reduce_bits(bits)
@@ -259,14 +260,30 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
     if rank != 0:
         return None
     peak, which = peaks()
-    # dominant kernel of the default (RLC) mode: k_bpoly_combine.  Algorithmic bytes per launch = the
-    # proofs' product tables it reads (16 KiB each) + the 2^k x 32 B combined vector it writes.
-    comb_ms = sum(k[0][1] + k[1][1] for k in kms) / a.steps
-    comb_bytes = (m * 16384 + (32 << 16)) + (2 * m * 16384 + (32 << 15))
-    comb_modmul = m * 65536 + 2 * m * 32768
-    # per-proof mode: k_accumulate, same formula as round 1 (96 B per MSM point)
-    acc_ms = sum(k[0][0] + k[1][0] for k in kms_pp) / pp_steps
-    acc_bytes = ALG_BYTES_PER_POINT * (m * 65536 + 2 * m * 32768)
+
+    def kernel_lines(stats, steps):
+        """roofline objects for k_accumulate (96 B per MSM point) and k_bpoly_combine (16 KiB of product
+        tables read per proof + one 2^k x 32 B vector written per slice) from the library's own CUDA-event sums"""
+        acc_ms = sum(x.accumulate_ms for pair in stats for x in pair) / steps
+        comb_ms = sum(x.combine_ms for pair in stats for x in pair) / steps
+        pts = sum(x.msm_points for pair in stats for x in pair) / steps
+        nmsm = sum(x.msm_count for pair in stats for x in pair) / steps
+        comb_bytes = sum(x.combine_proofs * 16384 + x.combine_vectors * (32 << (16 if i == 0 else 15)) for pair in stats for i, x in enumerate(pair)) / steps
+        comb_mod = sum(x.combine_proofs * (1 << (16 if i == 0 else 15)) for pair in stats for i, x in enumerate(pair)) / steps
+        acc = {"bound": "hbm", "achieved": ALG_BYTES_PER_POINT * pts / (acc_ms * 1e-3) / 1e9 if acc_ms else 0.0, "peak": peak, "unit": "GB/s",
+               "traffic": None, "kernel": "k_accumulate", "peak_source": which, "ms_per_step_in_kernel": acc_ms, "msms_per_step": nmsm,
+               "algorithmic_bytes_per_step": ALG_BYTES_PER_POINT * pts,
+               "note": "96 B x MSM points / summed k_accumulate CUDA-event time; integer-issue-bound: %.3g modmul/s (10 per mixed add, 16 adds per point)" % (160 * pts / (acc_ms * 1e-3) if acc_ms else 0)}
+        acc["frac"] = acc["achieved"] / peak
+        comb = {"bound": "hbm", "achieved": comb_bytes / (comb_ms * 1e-3) / 1e9 if comb_ms else 0.0, "peak": peak, "unit": "GB/s", "traffic": None,
+                "kernel": "k_bpoly_combine", "peak_source": which, "ms_per_step_in_kernel": comb_ms, "algorithmic_bytes_per_step": comb_bytes,
+                "note": "integer-issue-bound: %.3g modmul/s" % (comb_mod / (comb_ms * 1e-3) if comb_ms else 0)}
+        comb["frac"] = comb["achieved"] / peak
+        return acc, comb
+
+    acc_rlc, comb_rlc = kernel_lines(kms, a.steps)
+    acc_pp, _ = kernel_lines(kms_pp, pp_steps)
+    dominant = acc_rlc if acc_rlc["ms_per_step_in_kernel"] >= comb_rlc["ms_per_step_in_kernel"] else comb_rlc
     cores = os.cpu_count() or 1
     cpu, _ = cpu_verify_sample(proofs[6:8], pubs[6:8], cores)
     return {
@@ -277,15 +294,10 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
                    "mode": "rlc (random linear combination over the shard + bisection; per-proof numbers in `per_proof_mode`)",
                    "built_stages": BUILT, "absent_stages": ABSENT,
                    "l2": "per-step working set: %d x 16 KiB product tables + 64 MiB / 32 MiB fixed-base tables > 126 MB L2 together; inputs differ per proof only in 10 members" % (3 * m)},
-        "roofline": {"bound": "hbm", "achieved": comb_bytes / (comb_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": comb_bytes / (comb_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_bpoly_combine", "peak_source": which,
-                     "ms_per_step_in_kernel": comb_ms,
-                     "note": "integer-issue-bound: %.3g modmul/s in this kernel (see profiles/ for the measured modmul ceiling)" % (comb_modmul / (comb_ms * 1e-3))},
+        "roofline": dominant,
+        "other_kernels": [comb_rlc if dominant is acc_rlc else acc_rlc],
         "per_proof_mode": {"value": BATCH * pp_steps / t_pp, "e2e": BATCH * pp_steps / t_pp_e2e, "unit": UNIT, "steps": pp_steps,
-                           "roofline": {"bound": "hbm", "achieved": acc_bytes / (acc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                        "frac": acc_bytes / (acc_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_accumulate",
-                                        "ms_per_step_in_kernel": acc_ms,
-                                        "note": "96 B x MSM points / k_accumulate CUDA-event time (round-1 formula); modmul/s = %.3g" % (10 * 16 * (m * 65536 + 2 * m * 32768) / (acc_ms * 1e-3))}},
+                           "ms_per_step": t_pp / pp_steps * 1e3, "roofline": acc_pp},
         "cpu_baseline": {"value": cpu, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "2 proofs of the batch, per-proof MSMs; oracle/pasta_ref.c (arkworks window rule, 1 thread/window) + Python decoder; not the reference binary"},
         "e2e": {"value": BATCH * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": m * (256 + 64 + 480 + 128 + 3 * 32) + m,

@@ -118,9 +118,18 @@ int mina_b200_accumulator_check_batch(size_t n, const unsigned char *const *proo
 
 /* Device-resident variant (bench `value` leg): d_pre16 = m*k 16-byte prechallenges and d_pts64 = m
  * canonical affine points already in HBM (k = 16 on Vesta, 15 on Pallas); ok_host gets m bytes.
- * kernel_ms (may be NULL): float[2] = summed CUDA-event time of {k_accumulate, k_bpoly_combine}. */
+ * stats (may be NULL): CUDA-event time of the two dominant kernels summed over every launch of the call,
+ * and how much work those launches covered (for the roofline arithmetic in bench.py). */
+typedef struct {
+    float accumulate_ms;      /* k_accumulate, all chunks of all MSM batches */
+    float combine_ms;         /* k_bpoly_combine, all levels (RLC mode) */
+    uint64_t msm_points;      /* points summed by k_accumulate launches = sum over MSMs of n */
+    uint64_t msm_count;       /* MSMs over the resident SRS */
+    uint64_t combine_proofs;  /* proofs read by k_bpoly_combine launches (16 KiB of tables each) */
+    uint64_t combine_vectors; /* 2^k-element vectors written by k_bpoly_combine launches */
+} mina_b200_kernel_stats;
 int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, const void *d_pts64, int mode, uint8_t *ok_host,
-                                  float *kernel_ms);
+                                  mina_b200_kernel_stats *stats);
 
 /* ---- K4 / K2 / K5: IPA scalar helpers (host buffers, canonical 32-byte field elements) -------------- */
 /* ScalarChallenge::to_field for n 16-byte prechallenges landing in `field` (endo = that field's endo_r). */

@@ -526,7 +526,7 @@ int mina_b200_bpoly_combine(int field, uint32_t nproofs, int k, const uint8_t *c
         launch_fe_to_mont(field, d_in, d_m, (uint32_t)(nch + nproofs), c.stream);
         launch_bpoly_tables(field, d_m, d_t, nproofs, k, d_m + nch, false, c.stream);
     }
-    launch_bpoly_combine(field, d_t, nullptr, nproofs, k, d_o, c.stream);
+    launch_bpoly_combine(field, d_t, nullptr, nullptr, 0, nproofs, k, d_o, c.stream);
     c.launches += 3;
     CTX_CUDA_OK(cudaMemcpyAsync(out32, d_o, total * 32, cudaMemcpyDeviceToHost, c.stream));
     CTX_CUDA_OK(cudaStreamSynchronize(c.stream));

@@ -118,6 +118,7 @@ struct Context {
     bool time_accumulate = false;  // bench hook: sum the CUDA-event time of k_accumulate in per-proof mode
     float accumulate_ms = 0.f;
     float combine_ms = 0.f;        // same hook for k_bpoly_combine in RLC mode
+    uint64_t stat_msm_points = 0, stat_msm_count = 0, stat_combine_proofs = 0, stat_combine_vectors = 0;
     cudaEvent_t ev_combine[2] = {nullptr, nullptr};
     VerifierState *verifier = nullptr;  // owned; created / released by verifier.cu
 };

@@ -46,17 +46,18 @@ void launch_bpoly_materialize(int field, const fe *d_tables, fe *d_out, uint32_t
         k_bpoly_materialize<FqParams><<<g, 256, 0, s>>>(d_tables, d_out, nproofs, k);
 }
 
-void launch_bpoly_combine(int field, const fe *d_tables, const uint32_t *d_subset, uint32_t nsub, int k, fe *d_out,
-                          cudaStream_t s) {
+void launch_bpoly_combine(int field, const fe *d_tables, const uint32_t *d_subset, const uint32_t *d_group_off, uint32_t ngroups,
+                          uint32_t nsub, int k, fe *d_out, cudaStream_t s) {
     check_field(field);
     check_k(k);
     uint32_t n_hi = 1u << (k - BPOLY_LO_BITS);
     uint32_t threads = 256u * ((n_hi + COMBINE_ITEMS - 1) / COMBINE_ITEMS);
-    dim3 g((threads + 127) / 128);
+    dim3 g((threads + 127) / 128, ngroups ? ngroups : 1);
+    const uint32_t *goff = ngroups ? d_group_off : nullptr;
     if (field == 0)
-        k_bpoly_combine<FpParams><<<g, 128, 0, s>>>(d_tables, d_subset, nsub, k, d_out);
+        k_bpoly_combine<FpParams><<<g, 128, 0, s>>>(d_tables, d_subset, goff, nsub, k, d_out);
     else
-        k_bpoly_combine<FqParams><<<g, 128, 0, s>>>(d_tables, d_subset, nsub, k, d_out);
+        k_bpoly_combine<FqParams><<<g, 128, 0, s>>>(d_tables, d_subset, goff, nsub, k, d_out);
 }
 
 void launch_bpoly_eval(int field, const fe *d_chals, const fe *d_x, fe *d_out, uint32_t nproofs, uint32_t npts, int k,

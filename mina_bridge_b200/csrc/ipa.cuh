@@ -108,18 +108,27 @@ __global__ void __launch_bounds__(256) k_bpoly_materialize(const fe *__restrict_
 // once per proof; the 32 lanes of a warp read 32 consecutive lo entries (1 KiB, coalesced) and one
 // broadcast hi entry per proof.
 static constexpr int COMBINE_ITEMS = 4;
+// Several groups per launch (blockIdx.y = group): group g sums the proofs subset[group_off[g] ..
+// group_off[g+1]) into out + g * 2^k.  group_off == nullptr: one group of `nsub` proofs.
 template <class S>
 __global__ void __launch_bounds__(128) k_bpoly_combine(const fe *__restrict__ tables, const uint32_t *__restrict__ subset,
-                                                       uint32_t nsub, int k, fe *__restrict__ out) {
+                                                       const uint32_t *__restrict__ group_off, uint32_t nsub, int k,
+                                                       fe *__restrict__ out) {
     // thread -> (il, ih0): ih = ih0 * ITEMS + e
     const uint32_t n_hi = 1u << (k - BPOLY_LO_BITS);
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t il = tid & 255u, ih0 = (tid >> 8) * COMBINE_ITEMS;
     if (ih0 >= n_hi) return;
+    uint32_t begin = 0, end = nsub;
+    if (group_off) {
+        begin = group_off[blockIdx.y];
+        end = group_off[blockIdx.y + 1];
+        out += (size_t)blockIdx.y << k;
+    }
     fe acc[COMBINE_ITEMS];
 #pragma unroll
     for (int e = 0; e < COMBINE_ITEMS; e++) acc[e] = fe_zero();
-    for (uint32_t j = 0; j < nsub; j++) {
+    for (uint32_t j = begin; j < end; j++) {
         const fe *t = tables + (size_t)(subset ? subset[j] : j) * BPOLY_TABLE;
         fe lo = t[il];
 #pragma unroll
@@ -166,8 +175,9 @@ void launch_endo_to_field(int field, const void *d_pre16, fe *d_out, uint32_t n,
 void launch_bpoly_tables(int field, const fe *d_chals, fe *d_tables, uint32_t nproofs, int k, const fe *d_scale, bool lo_plain,
                          cudaStream_t s);
 void launch_bpoly_materialize(int field, const fe *d_tables, fe *d_out, uint32_t nproofs, int k, cudaStream_t s);
-void launch_bpoly_combine(int field, const fe *d_tables, const uint32_t *d_subset, uint32_t nsub, int k, fe *d_out,
-                          cudaStream_t s);
+// ngroups == 0: one group of nsub proofs (d_group_off ignored); else d_group_off[ngroups + 1] indexes d_subset
+void launch_bpoly_combine(int field, const fe *d_tables, const uint32_t *d_subset, const uint32_t *d_group_off, uint32_t ngroups,
+                          uint32_t nsub, int k, fe *d_out, cudaStream_t s);
 void launch_bpoly_eval(int field, const fe *d_chals, const fe *d_x, fe *d_out, uint32_t nproofs, uint32_t npts, int k,
                        cudaStream_t s);
 void launch_fe_to_mont(int field, const fe *d_in, fe *d_out, uint32_t n, cudaStream_t s);

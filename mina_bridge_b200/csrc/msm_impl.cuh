@@ -674,19 +674,17 @@ class MsmEngine : public MsmEngineBase {
         if (h) CUDA_OK(cudaMemsetAsync(err_, 0, sizeof h, s));
         return h;
     }
-    void enable_kernel_timing(bool on) override {
-        timing_ = on;
-        if (on && !ev0_) {
-            CUDA_OK(cudaEventCreate(&ev0_));
-            CUDA_OK(cudaEventCreate(&ev1_));
-        }
-    }
+    void enable_kernel_timing(bool on) override { timing_ = on; }
+    // sum over every chunk of the last run()/run_bpoly() call
     float last_accumulate_ms() override {
-        if (!timing_ || !ev0_) return 0.f;
-        float ms = 0.f;
-        CUDA_OK(cudaEventSynchronize(ev1_));
-        CUDA_OK(cudaEventElapsedTime(&ms, ev0_, ev1_));
-        return ms;
+        float total = 0.f;
+        for (size_t i = 0; i < ev_used_; i++) {
+            float ms = 0.f;
+            CUDA_OK(cudaEventSynchronize(ev_[2 * i + 1]));
+            CUDA_OK(cudaEventElapsedTime(&ms, ev_[2 * i], ev_[2 * i + 1]));
+            total += ms;
+        }
+        return total;
     }
 
    private:
@@ -716,9 +714,8 @@ class MsmEngine : public MsmEngineBase {
         free_dev(table_own_);
         drop_workspace();
         free_dev(err_);
-        if (ev0_) cudaEventDestroy(ev0_);
-        if (ev1_) cudaEventDestroy(ev1_);
-        ev0_ = ev1_ = nullptr;
+        for (cudaEvent_t e : ev_) cudaEventDestroy(e);
+        ev_.clear();
     }
 
     void run_src(int src, const uint32_t *d_src, int bpoly_k, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) {
@@ -737,6 +734,7 @@ class MsmEngine : public MsmEngineBase {
         if (chunk * buckets_per_msm >= (1ull << 32) || chunk * pairs_per_msm >= (1ull << 32))
             throw std::runtime_error("msm: problem too large for 32-bit indices");
         ensure_workspace((uint32_t)chunk, n_used);
+        ev_used_ = 0;
         for (uint32_t done = 0; done < nmsm; done += (uint32_t)chunk) {
             uint32_t cur = (uint32_t)std::min<uint64_t>(chunk, nmsm - done);
             const uint32_t *src_ptr = src == SRC_BPOLY ? d_src + (size_t)done * BPOLY_TABLE * 8 : d_src + (size_t)done * n_used * 8;
@@ -826,10 +824,20 @@ class MsmEngine : public MsmEngineBase {
         k_order_scan<<<1, 32, 0, s>>>(order_hist_);
         k_order_scatter<<<(nb + ORDER_BLOCK - 1) / ORDER_BLOCK, ORDER_BLOCK, 0, s>>>(offsets_, nb, order_hist_, order_);
         launches_ += 3;
-        if (timing_) CUDA_OK(cudaEventRecord(ev0_, s));
+        if (timing_) {
+            while (ev_.size() < 2 * (ev_used_ + 1)) {
+                cudaEvent_t e;
+                CUDA_OK(cudaEventCreate(&e));
+                ev_.push_back(e);
+            }
+            CUDA_OK(cudaEventRecord(ev_[2 * ev_used_], s));
+        }
         k_accumulate<F><<<(nb + 127) / 128, 128, 0, s>>>(order_, offsets_, pairs_, table_, buckets_, nb);
         launches_++;
-        if (timing_) CUDA_OK(cudaEventRecord(ev1_, s));
+        if (timing_) {
+            CUDA_OK(cudaEventRecord(ev_[2 * ev_used_ + 1], s));
+            ev_used_++;
+        }
         k_accumulate_overflow<F><<<296, OVER_THREADS, 0, s>>>(over_list_, order_hist_ + ORDER_BINS, offsets_, pairs_, table_, buckets_);
         launches_++;
 
@@ -874,7 +882,8 @@ class MsmEngine : public MsmEngineBase {
     size_t ws_bytes_ = 0;
     uint64_t launches_ = 0;
     bool timing_ = false;
-    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    std::vector<cudaEvent_t> ev_;  // (start, stop) per chunk of the last run
+    size_t ev_used_ = 0;
 };
 
 }  // namespace pasta

@@ -41,7 +41,7 @@ struct SideBuffers {  // one accumulator family (Vesta k=16 or Pallas k=15)
     PinnedBuf<uint8_t> h_pre, h_pts, h_r, h_out;
     PinnedBuf<uint32_t> h_subset;
     DevBuf<uint8_t> d_pre;
-    DevBuf<fe> d_chal, d_r_can, d_r, d_tab, d_S;
+    DevBuf<fe> d_chal, d_r_can, d_r, d_tab, d_S, d_partial;
     DevBuf<uint32_t> d_subset, d_pts_can, d_out_can, d_bad, d_sc;
     DevBuf<affine> d_pts, d_res;
 };
@@ -164,34 +164,66 @@ static void acc_per_proof(Context &c, SideBuffers &sb, AccumulatorBatch &ab) {
     c.launches += 3;
     CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_ok, ab.m, cudaMemcpyDeviceToHost, c.stream));
     if (cc.fixed->take_error(c.stream)) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
-    if (c.time_accumulate) c.accumulate_ms += cc.fixed->last_accumulate_ms();
+    if (c.time_accumulate) {
+        c.accumulate_ms += cc.fixed->last_accumulate_ms();
+        c.stat_msm_points += (uint64_t)ab.m << ab.k;
+        c.stat_msm_count += ab.m;
+    }
     for (uint32_t i = 0; i < ab.m; i++) ab.ok[i] = h_out[i];
 }
 
-// One random-linear-combination check over `subset` (indices into the batch).  Returns true iff
-//   < sum_j r_j b_poly_coefficients(chals_j), G > == sum_j r_j C_j.
-// The commitment side runs over ALL m points with r_j masked to zero outside the subset, so the bases
-// are converted and handed to the engine once per batch.
-static bool acc_rlc_check(Context &c, SideBuffers &sb, const AccumulatorBatch &ab, const std::vector<uint32_t> &subset) {
+// sum of the slices of each group: out[g][i] = sum_{s in [gso[g], gso[g+1])} partial[s][i]  (canonical)
+template <class S>
+static __global__ void __launch_bounds__(256) k_sum_slices(const fe *__restrict__ partial, const uint32_t *__restrict__ gso, int k,
+                                                           fe *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> k) return;
+    uint32_t s0 = gso[blockIdx.y], s1 = gso[blockIdx.y + 1];
+    fe acc = fe_zero();
+    for (uint32_t s = s0; s < s1; s++) acc = Fd<S>::add(acc, partial[((size_t)s << k) + i]);
+    out[((size_t)blockIdx.y << k) + i] = acc;
+}
+
+// One level of random-linear-combination checks, ALL groups in one launch set:
+//   pass[g]  <=>  < sum_{j in g} r_j b_poly_coefficients(chals_j), G >  ==  sum_{j in g} r_j C_j.
+// g side: k_bpoly_combine over slices of <= 64 proofs (so a single large group still fills the GPU),
+// k_sum_slices, then ONE batched MSM (nmsm = #groups) over the resident SRS.  Commitment side: one batched
+// MSM over the batch's own points with r_j masked to zero outside each group.
+static constexpr uint32_t COMBINE_SLICE = 64;
+static std::vector<uint8_t> acc_check_groups(Context &c, SideBuffers &sb, const AccumulatorBatch &ab,
+                                             const std::vector<std::vector<uint32_t>> &groups) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
-    const uint32_t ns = (uint32_t)subset.size();
-    uint32_t *h_sub = sb.h_subset.reserve(ns);
-    uint8_t *h_sc = sb.h_pts.reserve((size_t)ab.m * 32);
-    std::memset(h_sc, 0, (size_t)ab.m * 32);
-    for (uint32_t i = 0; i < ns; i++) {
-        h_sub[i] = subset[i];
-        std::memcpy(h_sc + 32 * (size_t)subset[i], sb.h_r.p + 32 * (size_t)subset[i], 32);
+    const uint32_t G = (uint32_t)groups.size();
+    std::vector<uint32_t> meta;  // subset | slice_off | group_slice_off, one upload
+    std::vector<uint32_t> slice_off{0}, gso{0};
+    for (auto &g : groups) {
+        for (size_t at = 0; at < g.size(); at += COMBINE_SLICE) {
+            size_t end = std::min(g.size(), at + COMBINE_SLICE);
+            meta.insert(meta.end(), g.begin() + at, g.begin() + end);
+            slice_off.push_back((uint32_t)meta.size());
+        }
+        gso.push_back((uint32_t)slice_off.size() - 1);
     }
-    uint32_t *d_sub = sb.d_subset.reserve(ns);
-    uint32_t *d_sc = sb.d_sc.reserve((size_t)ab.m * 8);
-    affine *d_res = sb.d_res.reserve(2);
-    uint32_t *d_can = sb.d_out_can.reserve(32);
-    fe *d_S = sb.d_S.reserve((size_t)1 << ab.k);
-    uint8_t *h_out = sb.h_out.reserve(128);
-    CTX_CUDA_OK(cudaMemcpyAsync(d_sub, h_sub, (size_t)ns * 4, cudaMemcpyHostToDevice, c.stream));
-    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, h_sc, (size_t)ab.m * 32, cudaMemcpyHostToDevice, c.stream));
-    // g side: S = sum_j r_j s_j, then one MSM over the resident SRS
+    const uint32_t nsubset = (uint32_t)meta.size(), S = (uint32_t)slice_off.size() - 1;
+    meta.insert(meta.end(), slice_off.begin(), slice_off.end());
+    meta.insert(meta.end(), gso.begin(), gso.end());
+    uint32_t *h_meta = sb.h_subset.reserve(meta.size());
+    std::memcpy(h_meta, meta.data(), meta.size() * 4);
+    uint8_t *h_sc = sb.h_pts.reserve((size_t)G * ab.m * 32);
+    std::memset(h_sc, 0, (size_t)G * ab.m * 32);
+    for (uint32_t g = 0; g < G; g++)
+        for (uint32_t j : groups[g]) std::memcpy(h_sc + 32 * ((size_t)g * ab.m + j), sb.h_r.p + 32 * (size_t)j, 32);
+    uint32_t *d_meta = sb.d_subset.reserve(meta.size());
+    uint32_t *d_sc = sb.d_sc.reserve((size_t)G * ab.m * 8);
+    affine *d_res = sb.d_res.reserve(2 * (size_t)G);
+    uint32_t *d_can = sb.d_out_can.reserve(32 * (size_t)G);
+    fe *d_S = sb.d_S.reserve((size_t)G << ab.k);
+    const bool sliced = S != G;
+    fe *d_partial = sliced ? sb.d_partial.reserve((size_t)S << ab.k) : d_S;
+    uint8_t *h_out = sb.h_out.reserve(128 * (size_t)G);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_meta, h_meta, meta.size() * 4, cudaMemcpyHostToDevice, c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, h_sc, (size_t)G * ab.m * 32, cudaMemcpyHostToDevice, c.stream));
     if (c.time_accumulate) {
         if (!c.ev_combine[0]) {
             CTX_CUDA_OK(cudaEventCreate(&c.ev_combine[0]));
@@ -199,15 +231,23 @@ static bool acc_rlc_check(Context &c, SideBuffers &sb, const AccumulatorBatch &a
         }
         CTX_CUDA_OK(cudaEventRecord(c.ev_combine[0], c.stream));
     }
-    launch_bpoly_combine(field, sb.d_tab.p, d_sub, ns, ab.k, d_S, c.stream);
+    launch_bpoly_combine(field, sb.d_tab.p, d_meta, d_meta + nsubset, S, nsubset, ab.k, d_partial, c.stream);
     if (c.time_accumulate) CTX_CUDA_OK(cudaEventRecord(c.ev_combine[1], c.stream));
+    c.launches += 1;
+    if (sliced) {
+        dim3 grid(((1u << ab.k) + 255) / 256, G);
+        if (field == 0)
+            k_sum_slices<FpParams><<<grid, 256, 0, c.stream>>>(d_partial, d_meta + nsubset + S + 1, ab.k, d_S);
+        else
+            k_sum_slices<FqParams><<<grid, 256, 0, c.stream>>>(d_partial, d_meta + nsubset + S + 1, ab.k, d_S);
+        c.launches += 1;
+    }
     cc.fixed->enable_kernel_timing(c.time_accumulate);
-    cc.fixed->run(reinterpret_cast<const uint32_t *>(d_S), 1, 1u << ab.k, d_res, c.stream);
-    // commitment side: sum_j r_j C_j over the batch's own points
-    cc.var->run(d_sc, 1, ab.m, d_res + 1, c.stream);
-    launch_affine_from_mont(ab.curve, d_res, d_can, 2, c.stream);
-    c.launches += 2;
-    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_can, 128, cudaMemcpyDeviceToHost, c.stream));
+    cc.fixed->run(reinterpret_cast<const uint32_t *>(d_S), G, 1u << ab.k, d_res, c.stream);
+    cc.var->run(d_sc, G, ab.m, d_res + G, c.stream);
+    launch_affine_from_mont(ab.curve, d_res, d_can, 2 * G, c.stream);
+    c.launches += 1;
+    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_can, 128 * (size_t)G, cudaMemcpyDeviceToHost, c.stream));
     uint32_t e = cc.fixed->take_error(c.stream) | cc.var->take_error(c.stream);  // synchronises
     if (e) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
     if (c.time_accumulate) {
@@ -215,30 +255,19 @@ static bool acc_rlc_check(Context &c, SideBuffers &sb, const AccumulatorBatch &a
         CTX_CUDA_OK(cudaEventElapsedTime(&ms, c.ev_combine[0], c.ev_combine[1]));
         c.combine_ms += ms;
         c.accumulate_ms += cc.fixed->last_accumulate_ms();
+        c.stat_msm_points += (uint64_t)G << ab.k;
+        c.stat_msm_count += G;
+        c.stat_combine_proofs += nsubset;
+        c.stat_combine_vectors += S;
     }
-    return std::memcmp(h_out, h_out + 64, 64) == 0;
+    std::vector<uint8_t> pass(G);
+    for (uint32_t g = 0; g < G; g++) pass[g] = std::memcmp(h_out + 64 * (size_t)g, h_out + 64 * ((size_t)G + g), 64) == 0;
+    return pass;
 }
 
-static void acc_bisect(Context &c, SideBuffers &sb, AccumulatorBatch &ab, const std::vector<uint32_t> &set, bool known_bad) {
-    if (set.empty()) return;
-    if (!known_bad && acc_rlc_check(c, sb, ab, set)) {
-        for (uint32_t i : set) ab.ok[i] = 1;
-        return;
-    }
-    if (set.size() == 1) {  // r != 0, so r*A == r*C  <=>  A == C: a failing singleton is a bad proof
-        ab.ok[set[0]] = 0;
-        return;
-    }
-    std::vector<uint32_t> left(set.begin(), set.begin() + set.size() / 2), right(set.begin() + set.size() / 2, set.end());
-    if (acc_rlc_check(c, sb, ab, left)) {
-        for (uint32_t i : left) ab.ok[i] = 1;
-        acc_bisect(c, sb, ab, right, true);  // the failure must be on the right
-    } else {
-        acc_bisect(c, sb, ab, left, true);
-        acc_bisect(c, sb, ab, right, false);
-    }
-}
-
+// Group testing in levels: the whole batch first (the common case ends here: one combine + one MSM), then
+// failing groups are split ~32-ways while they are large and 8-ways below 64, every level being ONE batched
+// launch set.  A failing singleton is a bad proof: r != 0, so r*A == r*C <=> A == C.
 static void acc_rlc(Context &c, SideBuffers &sb, AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
@@ -263,9 +292,26 @@ static void acc_rlc(Context &c, SideBuffers &sb, AccumulatorBatch &ab) {
     CTX_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
     CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
     if (bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
-    std::vector<uint32_t> all(ab.m);
-    for (uint32_t i = 0; i < ab.m; i++) all[i] = i;
-    acc_bisect(c, sb, ab, all, false);
+    std::vector<std::vector<uint32_t>> groups(1);
+    groups[0].resize(ab.m);
+    for (uint32_t i = 0; i < ab.m; i++) groups[0][i] = i;
+    while (!groups.empty()) {
+        std::vector<uint8_t> pass = acc_check_groups(c, sb, ab, groups);
+        std::vector<std::vector<uint32_t>> next;
+        for (size_t g = 0; g < groups.size(); g++) {
+            const std::vector<uint32_t> &grp = groups[g];
+            if (pass[g]) {
+                for (uint32_t i : grp) ab.ok[i] = 1;
+            } else if (grp.size() == 1) {
+                ab.ok[grp[0]] = 0;
+            } else {
+                size_t part = grp.size() > 64 ? (grp.size() + 31) / 32 : std::max<size_t>(1, grp.size() / 8);
+                for (size_t at = 0; at < grp.size(); at += part)
+                    next.emplace_back(grp.begin() + at, grp.begin() + std::min(grp.size(), at + part));
+            }
+        }
+        groups.swap(next);
+    }
 }
 
 static void run_accumulators(Context &c, AccumulatorBatch &ab, int mode) {
@@ -746,7 +792,7 @@ int mina_b200_accumulator_check_batch(size_t n, const unsigned char *const *proo
 // 16-byte prechallenges, d_pts64 = m canonical affine points (validated by the caller), k = 16 for
 // Vesta (curve 1) and 15 for Pallas (curve 0).  ok_host receives m bytes.  The call synchronises.
 int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, const void *d_pts64, int mode, uint8_t *ok_host,
-                                  float *kernel_ms) {
+                                  mina_b200_kernel_stats *stats) {
     try {
         require_ready();
         if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
@@ -759,9 +805,10 @@ int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, co
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
         CTX_CUDA_OK(cudaSetDevice(c.device));
-        c.time_accumulate = kernel_ms != nullptr;
+        c.time_accumulate = stats != nullptr;
         c.accumulate_ms = 0.f;
         c.combine_ms = 0.f;
+        c.stat_msm_points = c.stat_msm_count = c.stat_combine_proofs = c.stat_combine_vectors = 0;
         try {
             run_accumulators(c, ab, mode);
         } catch (...) {
@@ -769,9 +816,13 @@ int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, co
             throw;
         }
         c.time_accumulate = false;
-        if (kernel_ms) {
-            kernel_ms[0] = c.accumulate_ms;
-            kernel_ms[1] = c.combine_ms;
+        if (stats) {
+            stats->accumulate_ms = c.accumulate_ms;
+            stats->combine_ms = c.combine_ms;
+            stats->msm_points = c.stat_msm_points;
+            stats->msm_count = c.stat_msm_count;
+            stats->combine_proofs = c.stat_combine_proofs;
+            stats->combine_vectors = c.stat_combine_vectors;
         }
         if (m) std::memcpy(ok_host, ab.ok.data(), m);
         return 0;

@@ -369,12 +369,17 @@ def host_poseidon_permute(field: int, table: bytes, states: bytes) -> bytes:
 
 
 # ---- device-resident accumulator batches and the resident user base set (bench legs, config 2) ------------
-def accumulators_device(curve: int, m: int, d_pre: int, d_pts: int, mode: int = MODE_RLC, want_ms: bool = False):
+class KernelStats(ctypes.Structure):
+    _fields_ = [("accumulate_ms", ctypes.c_float), ("combine_ms", ctypes.c_float), ("msm_points", ctypes.c_uint64),
+                ("msm_count", ctypes.c_uint64), ("combine_proofs", ctypes.c_uint64), ("combine_vectors", ctypes.c_uint64)]
+
+
+def accumulators_device(curve: int, m: int, d_pre: int, d_pts: int, mode: int = MODE_RLC, want_stats: bool = False):
     ok = ctypes.create_string_buffer(max(m, 1))
-    ms = (ctypes.c_float * 2)()
+    st = KernelStats()
     _check(load().mina_b200_accumulators_device(curve, ctypes.c_uint32(m), ctypes.c_void_p(d_pre), ctypes.c_void_p(d_pts), mode, ok,
-                                                ms if want_ms else None))
-    return (ok.raw[:m], (ms[0], ms[1])) if want_ms else ok.raw[:m]
+                                                ctypes.byref(st) if want_stats else None))
+    return (ok.raw[:m], st) if want_stats else ok.raw[:m]
 
 
 def fixed_base_load(curve: int, points: bytes, window_bits: int = 0):
