@@ -180,7 +180,9 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
     import numpy as np
 
     proofs, pubs, want = synth_batch()
-    mine = list(range(rank, BATCH, world))
+    from mina_bridge_b200 import shard
+
+    mine = shard.shard_indices(BATCH, rank, world)
     my_proofs, my_pubs = [proofs[i] for i in mine], [pubs[i] for i in mine]
     m = len(mine)
     d_pre_w, d_pts_w, d_pre_s, d_pts_s = device_inputs(my_proofs, torch, dev)
@@ -191,11 +193,7 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
     def reduce_bits(bits):
         """per-proof result bytes -> the batch vector every rank ends up with (operator.go:461-465)"""
         pin.copy_(torch.frombuffer(bytearray(bits), dtype=torch.uint8))
-        result.fill_(1)
-        result[idx] = pin.to(dev, non_blocking=True)
-        if world > 1:
-            dist.all_reduce(result, op=dist.ReduceOp.MIN)
-        return result
+        return shard.merge_result_bytes(torch, dist, result, idx, pin.to(dev, non_blocking=True), world)
 
     def step_device(mode, timing=False):
         a1 = mb.accumulators_device(mb.CURVE_VESTA, m, d_pre_w.data_ptr(), d_pts_w.data_ptr(), mode, timing)

@@ -69,6 +69,10 @@ int mina_b200_msm(int curve, uint32_t n, const uint8_t *scalars32, const uint8_t
  * of the last chunk. */
 int mina_b200_msm_srs_device(int curve, uint32_t nmsm, uint32_t n, const void *d_scalars, void *d_out64,
                              void *cuda_stream, float *accumulate_ms);
+/* Shape of the IPA final-check MSM: sum_i s_i g[i] over the resident SRS prefix plus
+ * sum_j t_j P_j over a few caller-supplied points (canonical affine, validated).  Either part may be empty. */
+int mina_b200_msm_srs_plus(int curve, uint32_t n_srs, const uint8_t *scalars_srs32, uint32_t n_extra, const uint8_t *scalars_extra32,
+                           const uint8_t *points_extra64, uint8_t *out64);
 /* Fixed-base MSM over a caller-supplied base set that stays resident (BASELINE config 2: 2^20 Vesta
  * points): load once (builds the window table: ceil(255/c)+... x n x 64 B), then run any number of MSMs.
  * Points are validated (canonical, on curve).  window_bits 0 = 16. */
@@ -141,6 +145,11 @@ int mina_b200_bpoly_combine(int field, uint32_t nproofs, int k, const uint8_t *c
 /* b_poly(chals_j, x_{j,t}) for npts points per proof. */
 int mina_b200_bpoly_eval(int field, uint32_t nproofs, uint32_t npts, int k, const uint8_t *chals32, const uint8_t *x32, uint8_t *out32);
 
+/* kimchi combined_inner_product: sum_i polyscale^i sum_j evalscale^j evals[p][i][j]; scales32 = nproofs x
+ * (polyscale, evalscale). */
+int mina_b200_combined_inner_product(int field, uint32_t nproofs, uint32_t npolys, uint32_t npts, const uint8_t *evals32,
+                                      const uint8_t *scales32, uint8_t *out32);
+
 /* ---- K3: Poseidon (table-driven; see csrc/poseidon.hpp for the parity status of the constants) ------- */
 /* table = 174 x 32 bytes (MDS row-major, then 55 x 3 round constants).  states: n x 96 bytes, in place. */
 int mina_b200_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96);
@@ -165,6 +174,9 @@ int mina_b200_host_field_op(int field, int op, uint32_t n, const uint8_t *a32, c
 int mina_b200_host_srs_derive(int curve, uint32_t first, uint32_t count, uint8_t *out64, uint8_t *h64);
 /* Derive both SRS on the host and store them under cache_dir (what mina_b200_init loads). */
 int mina_b200_host_build_srs_cache(const char *cache_dir);
+/* Loader for the committed srs/{vesta,pallas}.srs files (MessagePack + compressed points):
+ * the first `count` points as canonical affine, and `h`.  -1 on a malformed file (see last_error). */
+int mina_b200_host_srs_load_file(int curve, const char *path, uint32_t count, uint8_t *out64, uint8_t *h64);
 int mina_b200_host_blake2b512(const uint8_t *data, size_t len, uint8_t out[64]);
 
 /* Wire decoders (csrc/wire.hpp).  kind: 0 state proof, 1 state pub, 2 account proof, 3 account pub.

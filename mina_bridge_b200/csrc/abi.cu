@@ -88,6 +88,12 @@ static host::Srs<B> load_or_create_srs(const std::string &dir, const char *name,
         path = dir + "/" + name + "_" + std::to_string(depth) + ".srsbin";
         if (host::srs_load_cache<B>(path, depth, srs)) return srs;
     }
+    // the committed file the bridge ships (srs/<name>.srs), if someone dropped it into the data directory
+    std::string err;
+    if (!dir.empty() && host::srs_load_file<B>(dir + "/" + name + ".srs", depth, srs, err) && host::srs_matches_pin<B>(srs)) {
+        host::srs_store_cache<B>(path, srs);
+        return srs;
+    }
     srs = host::srs_create<B>(depth);
     if (!host::srs_matches_pin<B>(srs)) throw std::runtime_error(std::string("SRS derivation does not match the pinned digest: ") + name);
     if (!path.empty()) host::srs_store_cache<B>(path, srs);  // best effort
@@ -552,6 +558,104 @@ int mina_b200_bpoly_eval(int field, uint32_t nproofs, uint32_t npts, int k, cons
     c.launches += 3;
     CTX_CUDA_OK(cudaMemcpyAsync(out32, d_oc, nx * 32, cudaMemcpyDeviceToHost, c.stream));
     CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+    ABI_CATCH
+}
+
+int mina_b200_combined_inner_product(int field, uint32_t nproofs, uint32_t npolys, uint32_t npts, const uint8_t *evals32,
+                                      const uint8_t *scales32, uint8_t *out32) {
+    ABI_TRY
+    require_ready();
+    if (!nproofs) return 0;
+    size_t ne = (size_t)nproofs * npolys * npts, ns = (size_t)nproofs * 2;
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    AbiScratch &sc = scratch();
+    fe *d_in = sc.a.reserve(ne + ns), *d_m = sc.b.reserve(ne + ns), *d_o = sc.c.reserve(nproofs), *d_oc = sc.d.reserve(nproofs);
+    if (ne) CTX_CUDA_OK(cudaMemcpyAsync(d_in, evals32, ne * 32, cudaMemcpyHostToDevice, c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_in + ne, scales32, ns * 32, cudaMemcpyHostToDevice, c.stream));
+    launch_fe_to_mont(field, d_in, d_m, (uint32_t)(ne + ns), c.stream);
+    launch_combined_inner_product(field, d_m, d_m + ne, d_o, nproofs, npolys, npts, c.stream);
+    launch_fe_from_mont(field, d_o, d_oc, nproofs, c.stream);
+    c.launches += 3;
+    CTX_CUDA_OK(cudaMemcpyAsync(out32, d_oc, (size_t)nproofs * 32, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+    ABI_CATCH
+}
+
+// Shape of the IPA final-check MSM: scalars over the resident SRS prefix g[0..n_srs) PLUS a
+// handful of per-proof points ({h, sg, U, C_k, L_j, R_j, delta}: ~80) in one result.
+int mina_b200_msm_srs_plus(int curve, uint32_t n_srs, const uint8_t *scalars_srs32, uint32_t n_extra, const uint8_t *scalars_extra32,
+                           const uint8_t *points_extra64, uint8_t *out64) {
+    ABI_TRY
+    require_ready();
+    if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    CurveCtx &cc = c.curve[curve];
+    if (n_srs > cc.depth) throw std::runtime_error("msm_srs_plus: n_srs exceeds the resident SRS depth");
+    AbiScratch &sc = scratch();
+    affine *d_res = sc.out.reserve(2);
+    uint32_t *d_can = sc.out_can.reserve(32);
+    uint8_t *d_bad = sc.bytes.reserve(4);
+    CTX_CUDA_OK(cudaMemsetAsync(d_res, 0, 2 * sizeof(affine), c.stream));
+    CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, c.stream));
+    if (n_srs) {
+        uint32_t *d_s = sc.scalars[0].reserve((size_t)n_srs * 8);
+        CTX_CUDA_OK(cudaMemcpyAsync(d_s, scalars_srs32, (size_t)n_srs * 32, cudaMemcpyHostToDevice, c.stream));
+        cc.fixed->enable_kernel_timing(false);
+        cc.fixed->run(d_s, 1, n_srs, d_res, c.stream);
+    }
+    if (n_extra) {
+        uint32_t *d_t = sc.scalars[1].reserve((size_t)n_extra * 8);
+        uint32_t *d_pc = sc.pts_can.reserve((size_t)n_extra * 16);
+        affine *d_p = sc.pts.reserve(n_extra);
+        CTX_CUDA_OK(cudaMemcpyAsync(d_t, scalars_extra32, (size_t)n_extra * 32, cudaMemcpyHostToDevice, c.stream));
+        CTX_CUDA_OK(cudaMemcpyAsync(d_pc, points_extra64, (size_t)n_extra * 64, cudaMemcpyHostToDevice, c.stream));
+        launch_affine_to_mont_checked(curve, d_pc, d_p, n_extra, (uint32_t *)d_bad, c.stream);
+        MsmConfig cfg;
+        cfg.precompute = false;
+        cfg.c = 8;
+        cc.var->set_bases(d_p, n_extra, cfg, c.stream);
+        cc.var->run(d_t, 1, n_extra, d_res + 1, c.stream);
+    }
+    launch_affine_from_mont(curve, d_res, d_can, 2, c.stream);
+    c.launches += 2;
+    uint8_t parts[128];
+    uint32_t bad = 0;
+    CTX_CUDA_OK(cudaMemcpyAsync(parts, d_can, 128, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
+    uint32_t e = (n_srs ? cc.fixed->take_error(c.stream) : 0) | (n_extra ? cc.var->take_error(c.stream) : 0);
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    if (e & 1u) throw std::runtime_error("msm: a scalar is >= 2^255 (not a canonical field element); result discarded");
+    if (bad) throw std::runtime_error("msm: a base point is non-canonical or not on the curve");
+    // the last addition of two points happens on the host
+    auto add2 = [&](auto tag) {
+        using B = decltype(tag);
+        auto load = [&](const uint8_t *b) {
+            host::Affine<B> a;
+            bool zero = true;
+            for (int i = 0; i < 64; i++) zero = zero && b[i] == 0;
+            if (zero) return host::Affine<B>::identity();
+            host::Fe<B>::from_bytes_le(b, a.x);
+            host::Fe<B>::from_bytes_le(b + 32, a.y);
+            a.inf = false;
+            return a;
+        };
+        host::Affine<B> r = host::Jac<B>::from_affine(load(parts)).add_affine(load(parts + 64)).to_affine();
+        std::memset(out64, 0, 64);
+        if (!r.inf) {
+            r.x.to_bytes_le(out64);
+            r.y.to_bytes_le(out64 + 32);
+        }
+    };
+    if (curve == 0)
+        add2(FpParams{});
+    else
+        add2(FqParams{});
     return 0;
     ABI_CATCH
 }

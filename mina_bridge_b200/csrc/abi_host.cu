@@ -119,6 +119,32 @@ int mina_b200_host_build_srs_cache(const char *cache_dir) {
     return 0;
 }
 
+int mina_b200_host_srs_load_file(int curve, const char *path, uint32_t count, uint8_t *out64, uint8_t *h64) {
+    std::string err;
+    auto emit = [&](auto &srs) {
+        for (uint32_t i = 0; i < count; i++) {
+            srs.g[i].x.to_bytes_le(out64 + 64 * (size_t)i);
+            srs.g[i].y.to_bytes_le(out64 + 64 * (size_t)i + 32);
+        }
+        if (h64) {
+            srs.h.x.to_bytes_le(h64);
+            srs.h.y.to_bytes_le(h64 + 32);
+        }
+    };
+    bool ok = false;
+    if (curve == 0) {
+        host::Srs<FpParams> srs;
+        if ((ok = host::srs_load_file<FpParams>(path, count, srs, err))) emit(srs);
+    } else if (curve == 1) {
+        host::Srs<FqParams> srs;
+        if ((ok = host::srs_load_file<FqParams>(path, count, srs, err))) emit(srs);
+    } else {
+        err = "bad curve id";
+    }
+    if (!ok) set_error(err);
+    return ok ? 0 : -1;
+}
+
 int mina_b200_host_blake2b512(const uint8_t *data, size_t len, uint8_t out[64]) {
     auto dg = host::Blake2b512::hash(data, len);
     std::memcpy(out, dg.data(), 64);

@@ -73,6 +73,17 @@ void launch_bpoly_eval(int field, const fe *d_chals, const fe *d_x, fe *d_out, u
         k_bpoly_eval<FqParams><<<g, 128, 0, s>>>(d_chals, d_x, d_out, nproofs, npts, k);
 }
 
+void launch_combined_inner_product(int field, const fe *d_evals, const fe *d_scales, fe *d_out, uint32_t nproofs, uint32_t npolys,
+                                   uint32_t npts, cudaStream_t s) {
+    check_field(field);
+    if (!nproofs) return;
+    dim3 g((nproofs + 127) / 128);
+    if (field == 0)
+        k_combined_inner_product<FpParams><<<g, 128, 0, s>>>(d_evals, d_scales, d_out, nproofs, npolys, npts);
+    else
+        k_combined_inner_product<FqParams><<<g, 128, 0, s>>>(d_evals, d_scales, d_out, nproofs, npolys, npts);
+}
+
 void launch_fe_to_mont(int field, const fe *d_in, fe *d_out, uint32_t n, cudaStream_t s) {
     check_field(field);
     if (!n) return;

@@ -158,6 +158,27 @@ __global__ void __launch_bounds__(128) k_bpoly_eval(const fe *__restrict__ chals
     out[idx] = acc;
 }
 
+// kimchi `combined_inner_product` (un-vendored poly-commitment @ 44e0d3b, every polynomial
+// has ONE chunk in the blockchain circuit and no degree-bound shift):
+//   cip = sum_i polyscale^i * ( sum_j evalscale^j * evals[i][j] ),  i < npolys, j < npts
+// evals: [nproofs][npolys][npts], scales: [nproofs][2] = (polyscale, evalscale); all Montgomery.
+// One thread per proof (47 x 2 terms: a serial Horner is the whole job).
+template <class S>
+__global__ void __launch_bounds__(128) k_combined_inner_product(const fe *__restrict__ evals, const fe *__restrict__ scales,
+                                                                fe *__restrict__ out, uint32_t nproofs, uint32_t npolys, uint32_t npts) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nproofs) return;
+    const fe polyscale = scales[2 * (size_t)p], evalscale = scales[2 * (size_t)p + 1];
+    const fe *e = evals + (size_t)p * npolys * npts;
+    fe acc = fe_zero();
+    for (int i = (int)npolys - 1; i >= 0; i--) {  // Horner in polyscale, inner Horner in evalscale
+        fe inner = fe_zero();
+        for (int j = (int)npts - 1; j >= 0; j--) inner = Fd<S>::add(Fd<S>::mul(inner, evalscale), e[(size_t)i * npts + j]);
+        acc = Fd<S>::add(Fd<S>::mul(acc, polyscale), inner);
+    }
+    out[p] = acc;
+}
+
 // canonical <-> Montgomery for flat arrays of field elements
 template <class S>
 __global__ void __launch_bounds__(256) k_fe_to_mont(const fe *__restrict__ in, fe *__restrict__ out, uint32_t n) {
@@ -180,6 +201,8 @@ void launch_bpoly_combine(int field, const fe *d_tables, const uint32_t *d_subse
                           uint32_t nsub, int k, fe *d_out, cudaStream_t s);
 void launch_bpoly_eval(int field, const fe *d_chals, const fe *d_x, fe *d_out, uint32_t nproofs, uint32_t npts, int k,
                        cudaStream_t s);
+void launch_combined_inner_product(int field, const fe *d_evals, const fe *d_scales, fe *d_out, uint32_t nproofs, uint32_t npolys,
+                                   uint32_t npts, cudaStream_t s);
 void launch_fe_to_mont(int field, const fe *d_in, fe *d_out, uint32_t n, cudaStream_t s);
 void launch_fe_from_mont(int field, const fe *d_in, fe *d_out, uint32_t n, cudaStream_t s);
 

@@ -98,6 +98,86 @@ Srs<B> srs_create(uint32_t depth, unsigned nthreads = 0) {
     return srs;
 }
 
+// The committed SRS files (srs/vesta.srs, srs/pallas.srs in the reference tree):
+// MessagePack `[ [bin(33) x n], bin(33) ]`, each 33-byte entry = ark-serialize 0.3 compressed point
+// (32 B x little-endian, flag byte 0x80 <=> y > (p-1)/2, 0x40 = infinity).  `want` points are taken from
+// the front (the Pallas side only ever uses the first 2^15 of the file's 2^16).
+template <class B>
+bool srs_decompress(const uint8_t *rec33, Affine<B> &out) {
+    if (rec33[32] & 0x40) return false;  // infinity never occurs in an SRS
+    if (rec33[32] & ~0x80u) return false;
+    Fe<B> x;
+    if (!Fe<B>::from_bytes_le(rec33, x)) return false;
+    Fe<B> y;
+    if (!(x.sqr() * x + Fe<B>::from_u64(5)).sqrt(y)) return false;
+    if (y.is_lexicographically_large() != ((rec33[32] & 0x80) != 0)) y = -y;
+    out.x = x;
+    out.y = y;
+    out.inf = false;
+    return true;
+}
+template <class B>
+bool srs_load_file(const std::string &path, uint32_t want, Srs<B> &out, std::string &err) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) {
+        err = "cannot open " + path;
+        return false;
+    }
+    std::vector<uint8_t> buf;
+    uint8_t chunk[1 << 16];
+    for (size_t n; (n = std::fread(chunk, 1, sizeof chunk, f)) > 0;) buf.insert(buf.end(), chunk, chunk + n);
+    std::fclose(f);
+    size_t o = 0;
+    auto need = [&](size_t k) { return o + k <= buf.size(); };
+    if (!need(1) || buf[o++] != 0x92) {
+        err = "not a 2-element MessagePack array";
+        return false;
+    }
+    uint64_t count = 0;
+    if (!need(1)) return false;
+    uint8_t tag = buf[o++];
+    if ((tag & 0xf0) == 0x90)
+        count = tag & 0x0f;
+    else if (tag == 0xdc && need(2)) {
+        count = ((uint64_t)buf[o] << 8) | buf[o + 1];
+        o += 2;
+    } else if (tag == 0xdd && need(4)) {
+        count = ((uint64_t)buf[o] << 24) | ((uint64_t)buf[o + 1] << 16) | ((uint64_t)buf[o + 2] << 8) | buf[o + 3];
+        o += 4;
+    } else {
+        err = "bad array header";
+        return false;
+    }
+    if (count < want) {
+        err = "file holds fewer points than requested";
+        return false;
+    }
+    if (!need((count + 1) * 35)) {
+        err = "truncated file";
+        return false;
+    }
+    const size_t first = o;
+    for (uint64_t i = 0; i <= count; i++)
+        if (buf[first + 35 * i] != 0xc4 || buf[first + 35 * i + 1] != 33) {
+            err = "entry is not bin8(33)";
+            return false;
+        }
+    out.g.resize(want);
+    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 64);
+    std::vector<std::thread> pool;
+    std::vector<int> bad(nthreads, 0);
+    for (unsigned t = 0; t < nthreads; t++)
+        pool.emplace_back([&, t]() {
+            for (uint32_t i = t; i < want; i += nthreads)
+                if (!srs_decompress<B>(&buf[first + 35 * (size_t)i + 2], out.g[i])) bad[t] = 1;
+        });
+    for (auto &th : pool) th.join();
+    bool ok = srs_decompress<B>(&buf[first + 35 * count + 2], out.h);
+    for (int b : bad) ok = ok && !b;
+    if (!ok) err = "a point failed to decompress";
+    return ok;
+}
+
 // Pinned digests of the derived SRS (Blake2b-512 over the (depth + 1) x 64-byte Montgomery payload:
 // g[0..depth) then h).  The same points are pinned independently in tests/golden/srs_sha256.json
 // against the reference's committed srs/{vesta,pallas}.srs.  The cache file is a trust root, so it

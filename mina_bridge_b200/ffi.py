@@ -398,3 +398,26 @@ def fixed_base_msm_device(curve: int, nmsm: int, d_scalars: int, d_out: int, str
     _check(load().mina_b200_fixed_base_msm_device(curve, ctypes.c_uint32(nmsm), ctypes.c_void_p(d_scalars), ctypes.c_void_p(d_out),
                                                   ctypes.c_void_p(stream), ctypes.byref(ms) if want_ms else None))
     return ms.value if want_ms else None
+
+
+def host_srs_load_file(curve: int, path: str, count: int):
+    out = ctypes.create_string_buffer(64 * max(count, 1))
+    h = ctypes.create_string_buffer(64)
+    rc = load().mina_b200_host_srs_load_file(curve, path.encode(), ctypes.c_uint32(count), out, h)
+    if rc != 0:
+        raise MinaB200Error(load().mina_b200_last_error().decode())
+    return out.raw[: 64 * count], h.raw
+
+
+def msm_srs_plus(curve: int, scalars_srs: bytes, scalars_extra: bytes, points_extra: bytes) -> bytes:
+    out = ctypes.create_string_buffer(64)
+    _check(load().mina_b200_msm_srs_plus(curve, ctypes.c_uint32(len(scalars_srs) // 32), scalars_srs, ctypes.c_uint32(len(scalars_extra) // 32),
+                                         scalars_extra, points_extra, out))
+    return out.raw
+
+
+def combined_inner_product(field: int, evals: bytes, scales: bytes, npolys: int, npts: int) -> bytes:
+    nproofs = len(scales) // 64
+    out = ctypes.create_string_buffer(32 * max(nproofs, 1))
+    _check(load().mina_b200_combined_inner_product(field, ctypes.c_uint32(nproofs), ctypes.c_uint32(npolys), ctypes.c_uint32(npts), evals, scales, out))
+    return out.raw[: 32 * nproofs]

@@ -264,3 +264,45 @@ def test_poseidon_is_untrusted_without_a_constants_table(gpu):
 
     have = os.path.exists(os.path.join(ROOT, "mina_bridge_b200", "data", "poseidon_fp_kimchi.bin"))
     assert gpu.poseidon_trusted() == have
+
+
+# ---- a9 shape and K5 ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cid", [0, 1])
+def test_msm_over_srs_prefix_plus_per_proof_points(gpu, cid):
+    """The IPA final-check MSM mixes the resident SRS prefix with ~80 per-proof points."""
+    rng = random.Random(90 + cid)
+    sm, fm = (pasta.Q, pasta.P) if cid == 0 else (pasta.P, pasta.Q)
+    n = 32768 if cid == 0 else 65536
+    srs, h = gpu.srs_points(cid, 0, n, True)
+    s1 = cref.ints_to_bytes([rng.randrange(sm) for _ in range(n)])
+    extra_pts = h + gpu.srs_points(cid, 5, 79)  # any on-curve points will do: h plus 79 more
+    s2 = cref.ints_to_bytes([rng.randrange(sm) for _ in range(79)] + [0])
+    want, _ = cref.msm(cid, s1 + s2, srs + extra_pts, 8)
+    assert gpu.msm_srs_plus(cid, s1, s2, extra_pts) == want
+    # either part empty; cancellation to the identity
+    w1, _ = cref.msm(cid, s1, srs, 8)
+    assert gpu.msm_srs_plus(cid, s1, b"", b"") == w1
+    w2, _ = cref.msm(cid, s2, extra_pts, 2)
+    assert gpu.msm_srs_plus(cid, b"", s2, extra_pts) == w2
+    g0 = srs[:64]
+    k = rng.randrange(sm)
+    assert gpu.msm_srs_plus(cid, cref.ints_to_bytes([k]), cref.ints_to_bytes([sm - k]), g0) == b"\0" * 64
+    with pytest.raises(gpu.MinaB200Error, match="not on the curve"):
+        gpu.msm_srs_plus(cid, s1, cref.ints_to_bytes([1]), b"\1" + b"\0" * 63)
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+def test_combined_inner_product(gpu, fid):
+    rng = random.Random(95 + fid)
+    m = FIELD_MOD[fid]
+    nproofs, npolys, npts = 5, 47, 2  # 47 polynomials at zeta, zeta*omega (SURVEY B.6)
+    evals = [[[rng.randrange(m) for _ in range(npts)] for _ in range(npolys)] for _ in range(nproofs)]
+    scales = [(rng.randrange(m), rng.randrange(m)) for _ in range(nproofs)]
+    scales[0] = (0, 5)
+    scales[1] = (7, 0)
+    got = gpu.combined_inner_product(fid, b"".join(cref.ints_to_bytes(row) for p in evals for row in p),
+                                     b"".join(cref.ints_to_bytes(s) for s in scales), npolys, npts)
+    for p in range(nproofs):
+        v, u = scales[p]
+        want = sum(pow(v, i, m) * sum(pow(u, j, m) * evals[p][i][j] for j in range(npts)) for i in range(npolys)) % m
+        assert int.from_bytes(got[32 * p : 32 * p + 32], "little") == want

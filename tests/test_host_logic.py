@@ -70,3 +70,57 @@ def test_host_srs_derivation_pinned(native):
         assert h.hex() == pins[name]["h"]
         g2, _ = cref.srs_derive(cid, 5000, 16, False)
         assert native.host_srs_derive(cid, 5000, 16) == g2
+
+
+def _write_srs_file(path, curve_id, points, h, array32=False):
+    """Producer side of srs/*.srs: MessagePack [[bin33 x n], bin33], compressed points."""
+    m = pasta.P if curve_id == 0 else pasta.Q
+
+    def rec(pt):
+        x, y = pt
+        return b"\xc4\x21" + x.to_bytes(32, "little") + (b"\x80" if y > (m - 1) // 2 else b"\x00")
+
+    n = len(points)
+    hdr = b"\x92" + (b"\xdd" + n.to_bytes(4, "big") if array32 or n > 0xFFFF else b"\xdc" + n.to_bytes(2, "big"))
+    open(path, "wb").write(hdr + b"".join(rec(p) for p in points) + rec(h))
+
+
+def test_srs_file_loader_round_trips_the_committed_format(native, tmp_path):
+    import pytest
+
+    for cid in (0, 1):
+        g, h = native.host_srs_derive(cid, 0, 700, True)
+        pts = [cref.bytes_to_point(g[64 * i : 64 * i + 64]) for i in range(700)]
+        for a32 in (False, True):
+            p = str(tmp_path / ("c%d_%d.srs" % (cid, a32)))
+            _write_srs_file(p, cid, pts, cref.bytes_to_point(h), a32)
+            got, got_h = native.host_srs_load_file(cid, p, 700)
+            assert got == g and got_h == h
+            got, _ = native.host_srs_load_file(cid, p, 300)  # a prefix, like Pallas' 2^15 of 2^16
+            assert got == g[: 64 * 300]
+            with pytest.raises(native.MinaB200Error):
+                native.host_srs_load_file(cid, p, 701)
+        raw = bytearray(open(p, "rb").read())
+        raw[10] ^= 1  # a corrupted x is (almost surely) not on the curve, or decompresses to another point
+        open(p, "wb").write(bytes(raw))
+        try:
+            got, _ = native.host_srs_load_file(cid, p, 700)
+            assert got != g
+        except native.MinaB200Error:
+            pass
+        open(p, "wb").write(bytes(raw[:1000]))
+        with pytest.raises(native.MinaB200Error):
+            native.host_srs_load_file(cid, p, 700)
+
+
+def test_srs_file_loader_on_the_reference_files_when_present(native):
+    """Here (not on the GPU box) the reference tree is mounted: its committed files must load to the pinned SRS."""
+    import pytest
+
+    pins = json.load(open(os.path.join(GOLDEN, "srs_sha256.json")))
+    for cid, name, depth in ((1, "vesta", 65536), (0, "pallas", 32768)):
+        path = "/root/reference/srs/%s.srs" % name
+        if not os.path.exists(path):
+            pytest.skip("reference tree not mounted")
+        g, h = native.host_srs_load_file(cid, path, depth)
+        assert hashlib.sha256(g).hexdigest() == pins[name]["sha256_g_%d" % depth] and h.hex() == pins[name]["h"]
