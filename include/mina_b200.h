@@ -135,6 +135,12 @@ typedef struct {
 int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, const void *d_pts64, int mode, uint8_t *ok_host,
                                   mina_b200_kernel_stats *stats);
 
+/* Both accumulator families of m state proofs at once, driven concurrently on two streams: d_pre_wrap =
+ * m x 16 prechallenges, d_pts_wrap = m points (Vesta); d_pre_step = 2m x 15 prechallenges, d_pts_step = 2m
+ * points (Pallas).  ok3 = 3 bytes per proof; stats2 (may be NULL) = {wrap, step}. */
+int mina_b200_state_accumulators_device(uint32_t m, const void *d_pre_wrap, const void *d_pts_wrap, const void *d_pre_step,
+                                        const void *d_pts_step, int mode, uint8_t *ok3, mina_b200_kernel_stats *stats2);
+
 /* ---- K4 / K2 / K5: IPA scalar helpers (host buffers, canonical 32-byte field elements) -------------- */
 /* ScalarChallenge::to_field for n 16-byte prechallenges landing in `field` (endo = that field's endo_r). */
 int mina_b200_endo_to_field(int field, uint32_t n, const uint8_t *pre16, uint8_t *out32);

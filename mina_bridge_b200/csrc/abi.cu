@@ -146,10 +146,6 @@ static void destroy_device_state(Context &c) {
         if (c.d_poseidon_tab[k]) cudaFree(c.d_poseidon_tab[k]);
         c.d_poseidon_tab[k] = nullptr;
     }
-    for (int i = 0; i < 2; i++) {
-        if (c.ev_combine[i]) cudaEventDestroy(c.ev_combine[i]);
-        c.ev_combine[i] = nullptr;
-    }
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     c.stream = c.copy_stream = nullptr;

@@ -99,7 +99,7 @@ struct Context {
     int device = -1;
     bool ready = false;
     cudaStream_t stream = nullptr;   // compute
-    cudaStream_t copy_stream = nullptr;  // H2D staging that overlaps compute
+    cudaStream_t copy_stream = nullptr;  // H2D staging that overlaps compute; second pipeline of a state batch
     CurveCtx curve[2];
     host::Srs<FpParams> srs_pallas;  // coordinates in Fp
     host::Srs<FqParams> srs_vesta;   // coordinates in Fq
@@ -115,11 +115,6 @@ struct Context {
     fe *d_poseidon_tab[2] = {nullptr, nullptr};
     std::mutex mu;  // the device lock: one GPU work item (a whole coalesced batch) at a time
     std::atomic<uint64_t> launches{0};
-    bool time_accumulate = false;  // bench hook: sum the CUDA-event time of k_accumulate in per-proof mode
-    float accumulate_ms = 0.f;
-    float combine_ms = 0.f;        // same hook for k_bpoly_combine in RLC mode
-    uint64_t stat_msm_points = 0, stat_msm_count = 0, stat_combine_proofs = 0, stat_combine_vectors = 0;
-    cudaEvent_t ev_combine[2] = {nullptr, nullptr};
     VerifierState *verifier = nullptr;  // owned; created / released by verifier.cu
 };
 

@@ -354,22 +354,9 @@ struct Fd {
             : "+r"(b0), "+r"(b1), "+r"(k)
             : "r"(m), "r"(F::MOD(2)));
     }
-    static __device__ __forceinline__ fe mul_ptx2(const fe &a, const fe &b) {
-        uint32_t X[17], Y[17];
-#pragma unroll
-        for (int i = 8; i < 17; i++) X[i] = Y[i] = 0;
-        mul_row(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
-        mul_row(Y, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
-#pragma unroll
-        for (int i = 1; i < 8; i++) {
-            if (i & 1) {
-                mad_row(&Y[i - 1], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
-                mad_row(&X[i + 1], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
-            } else {
-                mad_row(&X[i], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
-                mad_row(&Y[i], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
-            }
-        }
+    // Reduction of a product held in the two parity accumulators (true value = X + (Y << 32), X[16] and
+    // Y[14] are the top carry limbs).  Consumes X and Y.
+    static __device__ __forceinline__ fe redc2(uint32_t *X, uint32_t *Y) {
         // Ordering only: without this data dependency ptxas interleaves the reduction rounds with the
         // product rows, keeps a dozen carry chains alive at once and spills predicates (35 P2R + 43 ISETP
         // per multiplication measured); with it at most three chains are live.
@@ -442,6 +429,122 @@ struct Fd {
         return cond_sub_p(r);
     }
 
+    static __device__ __forceinline__ fe mul_ptx2(const fe &a, const fe &b) {
+        uint32_t X[17], Y[17];
+#pragma unroll
+        for (int i = 8; i < 17; i++) X[i] = Y[i] = 0;
+        mul_row(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+        mul_row(Y, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            if (i & 1) {
+                mad_row(&Y[i - 1], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+                mad_row(&X[i + 1], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+            } else {
+                mad_row(&X[i], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+                mad_row(&Y[i], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+            }
+        }
+        return redc2(X, Y);
+    }
+
+    // acc[0..4) += (a0, a1) * b, carry into acc[4]; acc[0..6) += (a0, a1, a2) * b, carry into acc[6]
+    static __device__ __forceinline__ void mad_row2(uint32_t *acc, uint32_t a0, uint32_t a1, uint32_t b) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, %4, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+            : "r"(a0), "r"(a1), "r"(b));
+    }
+    static __device__ __forceinline__ void mad_row3(uint32_t *acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+            "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32 %6, %6, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+    }
+    // Dedicated squaring: the 28 off-diagonal products a_i*a_j (i < j) are computed once and doubled
+    // (36 IMAD.WIDE for the product instead of 64; the doubling is 30 funnel shifts on the ALU pipe,
+    // which has slack while the multiply pipe is the bottleneck).  Same parity accumulators as
+    // mul_ptx2: Y collects the 16 (even, odd) pairs, X the 6 (even, even) pairs, Z the 6 (odd, odd)
+    // pairs (rows must move upward so a row's carry limb is always untouched above; the two X-parity
+    // families interleave, hence the third accumulator, merged with one add chain).
+    static __device__ __forceinline__ fe sqr_ptx2(const fe &a) {
+        uint32_t X[17], Y[17], Z[15];
+#pragma unroll
+        for (int i = 0; i < 17; i++) X[i] = Y[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 15; i++) Z[i] = 0;
+        // (even, odd) pairs: true limb e + o = Y index e + o - 1
+        mul_row(Y, a.v[0], a.v[2], a.v[4], a.v[6], a.v[1]);
+        mad_row(&Y[2], a.v[0], a.v[2], a.v[4], a.v[6], a.v[3]);
+        mad_row(&Y[4], a.v[0], a.v[2], a.v[4], a.v[6], a.v[5]);
+        mad_row(&Y[6], a.v[0], a.v[2], a.v[4], a.v[6], a.v[7]);
+        // (even, even) pairs into X, (odd, odd) pairs into Z
+        {
+            uint64_t p = (uint64_t)a.v[0] * a.v[2];
+            X[2] = (uint32_t)p;
+            X[3] = (uint32_t)(p >> 32);
+            uint64_t q = (uint64_t)a.v[1] * a.v[3];
+            Z[4] = (uint32_t)q;
+            Z[5] = (uint32_t)(q >> 32);
+        }
+        mad_row2(&X[4], a.v[0], a.v[2], a.v[4]);
+        mad_row3(&X[6], a.v[0], a.v[2], a.v[4], a.v[6]);
+        mad_row2(&Z[6], a.v[1], a.v[3], a.v[5]);
+        mad_row3(&Z[8], a.v[1], a.v[3], a.v[5], a.v[7]);
+        asm("add.cc.u32 %0, %0, %12;\n\t"
+            "addc.cc.u32 %1, %1, %13;\n\t"
+            "addc.cc.u32 %2, %2, %14;\n\t"
+            "addc.cc.u32 %3, %3, %15;\n\t"
+            "addc.cc.u32 %4, %4, %16;\n\t"
+            "addc.cc.u32 %5, %5, %17;\n\t"
+            "addc.cc.u32 %6, %6, %18;\n\t"
+            "addc.cc.u32 %7, %7, %19;\n\t"
+            "addc.cc.u32 %8, %8, %20;\n\t"
+            "addc.cc.u32 %9, %9, %21;\n\t"
+            "addc.cc.u32 %10, %10, %22;\n\t"
+            "addc.u32 %11, %11, 0;"
+            : "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(X[12]),
+              "+r"(X[13]), "+r"(X[14]), "+r"(X[15])
+            : "r"(Z[4]), "r"(Z[5]), "r"(Z[6]), "r"(Z[7]), "r"(Z[8]), "r"(Z[9]), "r"(Z[10]), "r"(Z[11]), "r"(Z[12]), "r"(Z[13]),
+              "r"(Z[14]));
+        // double the off-diagonal sums
+#pragma unroll
+        for (int k = 15; k >= 3; k--) X[k] = __funnelshift_l(X[k - 1], X[k], 1);
+        X[2] <<= 1;
+#pragma unroll
+        for (int k = 15; k >= 1; k--) Y[k] = __funnelshift_l(Y[k - 1], Y[k], 1);
+        Y[0] <<= 1;
+        // diagonal a_i^2 at true limbs 2i, 2i+1: one 16-limb chain
+        asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+            "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+            "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+            "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+            "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+            "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+            "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+            "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+            "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+            "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+            "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+            "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+            "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+            "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+            "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+            "madc.hi.u32 %15, %23, %23, %15;"
+            : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(X[8]), "+r"(X[9]),
+              "+r"(X[10]), "+r"(X[11]), "+r"(X[12]), "+r"(X[13]), "+r"(X[14]), "+r"(X[15])
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+        return redc2(X, Y);
+    }
+
     static __device__ __forceinline__ fe add_ptx(const fe &a, const fe &b) {
         uint32_t r[8];
         asm("add.cc.u32 %0, %8, %16;\n\t"
@@ -498,7 +601,13 @@ struct Fd {
         return mul_portable(a, b);
 #endif
     }
-    PASTA_HD static fe sqr(const fe &a) { return mul(a, a); }
+    PASTA_HD static fe sqr(const fe &a) {
+#ifdef __CUDA_ARCH__
+        return sqr_ptx2(a);
+#else
+        return mul_portable(a, a);
+#endif
+    }
     PASTA_HD static fe add(const fe &a, const fe &b) {
 #ifdef __CUDA_ARCH__
         return add_ptx(a, b);

@@ -29,6 +29,9 @@ class MsmEngineBase {
     // Same, but MSM m takes its 2^k scalars from b_poly_coefficients of proof m, given as the proof's
     // two product tables (ipa.cuh: lo plain, hi Montgomery); the coefficient vector is never stored.
     virtual void run_bpoly(const fe *d_tables, uint32_t nmsm, int k, affine *d_out, cudaStream_t s) = 0;
+    // Same two entry points without the final normalisation: results stay in XYZZ form (no inversion).
+    virtual void run_xyzz(const uint32_t *d_scalars, uint32_t nmsm, uint32_t n_used, xyzz *d_out, cudaStream_t s) = 0;
+    virtual void run_bpoly_xyzz(const fe *d_tables, uint32_t nmsm, int k, xyzz *d_out, cudaStream_t s) = 0;
     virtual size_t workspace_bytes() const = 0;
     // kernels launched by this engine since construction (counted where they are issued)
     virtual uint64_t launches() const = 0;

@@ -245,6 +245,10 @@ template <class F>
 __device__ __noinline__ fe mul_call(const fe a, const fe b) {
     return Fd<F>::mul(a, b);
 }
+template <class F>
+__device__ __noinline__ fe sqr_call(const fe a) {
+    return Fd<F>::sqr(a);
+}
 // Ec<F>::add_mixed with the multiplications out of line (same formulas, "madd-2008-s")
 template <class F>
 __device__ __forceinline__ void add_mixed_compact(xyzz &p, const affine &q) {
@@ -265,10 +269,10 @@ __device__ __forceinline__ void add_mixed_compact(xyzz &p, const affine &q) {
             p = Ec<F>::identity();
         return;
     }
-    fe PP = mul_call<F>(P, P);
+    fe PP = sqr_call<F>(P);
     fe PPP = mul_call<F>(P, PP);
     fe Q = mul_call<F>(p.x, PP);
-    fe X3 = fd::sub(fd::sub(mul_call<F>(R, R), PPP), fd::dbl(Q));
+    fe X3 = fd::sub(fd::sub(sqr_call<F>(R), PPP), fd::dbl(Q));
     fe Y3 = fd::sub(mul_call<F>(R, fd::sub(Q, X3)), mul_call<F>(p.y, PPP));
     p.x = X3;
     p.y = Y3;
@@ -343,21 +347,25 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const uint32_t *__restric
     if (end - k > ACC_SEG) end = k + ACC_SEG;
     xyzz acc = Ec<F>::identity();
     if (k < end) {
+        // software pipeline: the point for step k+1 and the table index for step k+2 are in flight while
+        // step k's ~2.3k integer instructions run (index -> point is a dependent pair of loads)
         uint32_t e = pairs[k];
+        uint32_t e_next = (k + 1 < end) ? pairs[k + 1] : 0u;
         affine q = load_point<F>(table, e);
         for (;;) {
-            uint32_t e_next = 0;
+            uint32_t e_next2 = 0;
             affine q_next;
             bool more = (k + 1 < end);
             if (more) {
-                e_next = pairs[k + 1];
                 q_next = load_point<F>(table, e_next);
+                if (k + 2 < end) e_next2 = pairs[k + 2];
             }
             if (e >> 31) q.y = Fd<F>::neg(q.y);
             add_mixed_compact<F>(acc, q);
             if (!more) break;
             q = q_next;
             e = e_next;
+            e_next = e_next2;
             k++;
         }
     }
@@ -481,10 +489,12 @@ struct FinalParams {
 };
 // One thread per MSM: unwind the reduction levels, combine windows, normalise to affine.
 //   D_last = sumW[last];  D_l = sumW[l] + m_l * (D_{l+1} - T),  T = sum of all buckets of the group.
-template <class F>
+// AFFINE = false leaves the result in XYZZ form (no field inversion): callers that only COMPARE results
+// (the accumulator checks) cross-multiply instead of normalising.
+template <class F, bool AFFINE>
 __global__ void __launch_bounds__(64) k_finalize(const xyzz *__restrict__ sumW /* [levels][groups] */,
                                                  const xyzz *__restrict__ total /* [groups] */, FinalParams fp,
-                                                 affine *__restrict__ out, uint32_t nmsm) {
+                                                 void *__restrict__ out_any, uint32_t nmsm) {
     uint32_t msm = blockIdx.x * blockDim.x + threadIdx.x;
     if (msm >= nmsm) return;
     xyzz res = Ec<F>::identity();
@@ -502,7 +512,10 @@ __global__ void __launch_bounds__(64) k_finalize(const xyzz *__restrict__ sumW /
             for (int k = 0; k < fp.c; k++) res = Ec<F>::dbl(res);
         Ec<F>::add(res, D);
     }
-    out[msm] = Ec<F>::to_affine(res);
+    if (AFFINE)
+        reinterpret_cast<affine *>(out_any)[msm] = Ec<F>::to_affine(res);
+    else
+        reinterpret_cast<xyzz *>(out_any)[msm] = res;
 }
 
 // ---- fixed-base table: T[w] = 2^c * T[w-1], normalised to affine (one Fermat inversion per point) ----
@@ -657,11 +670,18 @@ class MsmEngine : public MsmEngineBase {
     }
 
     void run(const uint32_t *d_scalars, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) override {
-        run_src(SRC_MEMORY, d_scalars, 0, nmsm, n_used, d_out, s);
+        run_src(SRC_MEMORY, d_scalars, 0, nmsm, n_used, d_out, true, s);
     }
     void run_bpoly(const fe *d_tables, uint32_t nmsm, int k, affine *d_out, cudaStream_t s) override {
         if (k < BPOLY_LO_BITS || k > 2 * BPOLY_LO_BITS) throw std::runtime_error("msm: bpoly rounds must be in [8, 16]");
-        run_src(SRC_BPOLY, reinterpret_cast<const uint32_t *>(d_tables), k, nmsm, 1u << k, d_out, s);
+        run_src(SRC_BPOLY, reinterpret_cast<const uint32_t *>(d_tables), k, nmsm, 1u << k, d_out, true, s);
+    }
+    void run_xyzz(const uint32_t *d_scalars, uint32_t nmsm, uint32_t n_used, xyzz *d_out, cudaStream_t s) override {
+        run_src(SRC_MEMORY, d_scalars, 0, nmsm, n_used, d_out, false, s);
+    }
+    void run_bpoly_xyzz(const fe *d_tables, uint32_t nmsm, int k, xyzz *d_out, cudaStream_t s) override {
+        if (k < BPOLY_LO_BITS || k > 2 * BPOLY_LO_BITS) throw std::runtime_error("msm: bpoly rounds must be in [8, 16]");
+        run_src(SRC_BPOLY, reinterpret_cast<const uint32_t *>(d_tables), k, nmsm, 1u << k, d_out, false, s);
     }
 
     size_t workspace_bytes() const override { return ws_bytes_ + (table_own_ ? (size_t)W_ * n_bases_ * sizeof(affine) : 0); }
@@ -718,7 +738,7 @@ class MsmEngine : public MsmEngineBase {
         ev_.clear();
     }
 
-    void run_src(int src, const uint32_t *d_src, int bpoly_k, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) {
+    void run_src(int src, const uint32_t *d_src, int bpoly_k, uint32_t nmsm, uint32_t n_used, void *d_out, bool affine_out, cudaStream_t s) {
         if (!table_) throw std::runtime_error("msm: no bases set");
         if (n_used > n_bases_) throw std::runtime_error("msm: n_used exceeds resident bases");
         if (nmsm == 0) return;
@@ -738,7 +758,8 @@ class MsmEngine : public MsmEngineBase {
         for (uint32_t done = 0; done < nmsm; done += (uint32_t)chunk) {
             uint32_t cur = (uint32_t)std::min<uint64_t>(chunk, nmsm - done);
             const uint32_t *src_ptr = src == SRC_BPOLY ? d_src + (size_t)done * BPOLY_TABLE * 8 : d_src + (size_t)done * n_used * 8;
-            run_chunk(src, src_ptr, bpoly_k, cur, n_used, d_out + done, s);
+            void *out_ptr = affine_out ? (void *)(reinterpret_cast<affine *>(d_out) + done) : (void *)(reinterpret_cast<xyzz *>(d_out) + done);
+            run_chunk(src, src_ptr, bpoly_k, cur, n_used, out_ptr, affine_out, s);
         }
     }
 
@@ -794,7 +815,7 @@ class MsmEngine : public MsmEngineBase {
         launches_++;
     }
 
-    void run_chunk(int src, const uint32_t *d_src, int bpoly_k, uint32_t nmsm, uint32_t n_used, affine *d_out, cudaStream_t s) {
+    void run_chunk(int src, const uint32_t *d_src, int bpoly_k, uint32_t nmsm, uint32_t n_used, void *d_out, bool affine_out, cudaStream_t s) {
         DigitParams dp;
         dp.n_used = n_used;
         dp.n_bases = n_bases_;
@@ -863,7 +884,10 @@ class MsmEngine : public MsmEngineBase {
         fp.W = cfg_.precompute ? 1 : W_;
         fp.c = cfg_.c;
         fp.groups = groups;
-        k_finalize<F><<<(nmsm + 63) / 64, 64, 0, s>>>(sumW_, last_S, fp, d_out, nmsm);
+        if (affine_out)
+            k_finalize<F, true><<<(nmsm + 63) / 64, 64, 0, s>>>(sumW_, last_S, fp, d_out, nmsm);
+        else
+            k_finalize<F, false><<<(nmsm + 63) / 64, 64, 0, s>>>(sumW_, last_S, fp, d_out, nmsm);
         launches_++;
         CUDA_OK(cudaGetLastError());
     }

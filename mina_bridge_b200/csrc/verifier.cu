@@ -44,6 +44,7 @@ struct SideBuffers {  // one accumulator family (Vesta k=16 or Pallas k=15)
     DevBuf<fe> d_chal, d_r_can, d_r, d_tab, d_S, d_partial;
     DevBuf<uint32_t> d_subset, d_pts_can, d_out_can, d_bad, d_sc;
     DevBuf<affine> d_pts, d_res;
+    DevBuf<xyzz> d_xyzz;
 };
 struct VerifierState {
     SideBuffers side[2];  // index = curve id: 0 Pallas (step accumulators), 1 Vesta (wrap accumulator)
@@ -119,12 +120,57 @@ static __global__ void __launch_bounds__(256) k_points_equal(const uint4 *__rest
     ok[i] = diff == 0;
 }
 
+// res[i] (XYZZ) == claimed affine point (canonical bytes), without normalising res:
+//   x = X/ZZ, y = Y/ZZZ  <=>  X == x*ZZ and Y == y*ZZZ   (the claimed point is never the identity)
+template <class F>
+static __global__ void __launch_bounds__(128) k_xyzz_equals_affine(const xyzz *__restrict__ res, const uint32_t *__restrict__ pts_can,
+                                                                   uint32_t m, uint8_t *__restrict__ ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    xyzz r = res[i];
+    fe x, y;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        x.v[k] = pts_can[(size_t)i * 16 + k];
+        y.v[k] = pts_can[(size_t)i * 16 + 8 + k];
+    }
+    x = Fd<F>::to_mont(x);
+    y = Fd<F>::to_mont(y);
+    bool good = !fe_is_zero(r.zz) && fe_eq(r.x, Fd<F>::mul(x, r.zz)) && fe_eq(r.y, Fd<F>::mul(y, r.zzz));
+    ok[i] = good ? 1 : 0;
+}
+// a[g] == b[g] for two XYZZ arrays (cross-multiplication; identity == identity)
+template <class F>
+static __global__ void __launch_bounds__(128) k_xyzz_pairs_equal(const xyzz *__restrict__ a, const xyzz *__restrict__ b, uint32_t n,
+                                                                 uint8_t *__restrict__ ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xyzz p = a[i], q = b[i];
+    bool pi = fe_is_zero(p.zz), qi = fe_is_zero(q.zz);
+    bool good;
+    if (pi || qi)
+        good = pi && qi;
+    else
+        good = fe_eq(Fd<F>::mul(p.x, q.zz), Fd<F>::mul(q.x, p.zz)) && fe_eq(Fd<F>::mul(p.y, q.zzz), Fd<F>::mul(q.y, p.zzz));
+    ok[i] = good ? 1 : 0;
+}
+
+// One accumulator family runs on its own stream with its own statistics, so the Vesta and the Pallas
+// pipelines of a batch can be driven by two host threads and overlap on the device (their MSM tails are
+// latency-bound and leave most SMs idle).
+struct AccRun {
+    cudaStream_t s = nullptr;
+    bool timing = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    mina_b200_kernel_stats stats{0.f, 0.f, 0, 0, 0, 0};
+};
+
 struct AccDevice {  // device views of one prepared batch
     const uint8_t *d_pre = nullptr;
     const uint32_t *d_pts_can = nullptr;
 };
 
-static AccDevice acc_prepare(Context &c, SideBuffers &sb, const AccumulatorBatch &ab) {
+static AccDevice acc_prepare(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;  // scalar field of the curve
     const size_t npre = (size_t)ab.m * ab.k;
     AccDevice dv;
@@ -136,38 +182,38 @@ static AccDevice acc_prepare(Context &c, SideBuffers &sb, const AccumulatorBatch
         std::memcpy(h_pre, ab.pre.data(), npre * 16);
         std::memcpy(h_pre + npre * 16, ab.pts.data(), (size_t)ab.m * 64);
         uint8_t *d_pre = sb.d_pre.reserve(npre * 16 + (size_t)ab.m * 64);
-        CTX_CUDA_OK(cudaMemcpyAsync(d_pre, h_pre, npre * 16 + (size_t)ab.m * 64, cudaMemcpyHostToDevice, c.stream));
+        CTX_CUDA_OK(cudaMemcpyAsync(d_pre, h_pre, npre * 16 + (size_t)ab.m * 64, cudaMemcpyHostToDevice, rs.s));
         dv.d_pre = d_pre;
         dv.d_pts_can = reinterpret_cast<const uint32_t *>(d_pre + npre * 16);
     }
     fe *d_chal = sb.d_chal.reserve(npre);
-    launch_endo_to_field(field, dv.d_pre, d_chal, (uint32_t)npre, c.stream);
+    launch_endo_to_field(field, dv.d_pre, d_chal, (uint32_t)npre, rs.s);
     c.launches += 1;
     return dv;
 }
 
-static void acc_per_proof(Context &c, SideBuffers &sb, AccumulatorBatch &ab) {
+static void acc_per_proof(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
-    AccDevice dv = acc_prepare(c, sb, ab);
+    AccDevice dv = acc_prepare(c, rs, sb, ab);
     fe *d_tab = sb.d_tab.reserve((size_t)ab.m * BPOLY_TABLE);
-    affine *d_res = sb.d_res.reserve(ab.m);
-    uint32_t *d_can = sb.d_out_can.reserve((size_t)ab.m * 16);
+    xyzz *d_res = sb.d_xyzz.reserve(ab.m);
     uint8_t *d_ok = reinterpret_cast<uint8_t *>(sb.d_subset.reserve((ab.m + 3) / 4));
     uint8_t *h_out = sb.h_out.reserve(ab.m);
-    launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, nullptr, true, c.stream);
-    cc.fixed->enable_kernel_timing(c.time_accumulate);
-    cc.fixed->run_bpoly(d_tab, ab.m, ab.k, d_res, c.stream);
-    launch_affine_from_mont(ab.curve, d_res, d_can, ab.m, c.stream);
-    k_points_equal<<<(ab.m + 255) / 256, 256, 0, c.stream>>>(reinterpret_cast<const uint4 *>(d_can),
-                                                              reinterpret_cast<const uint4 *>(dv.d_pts_can), ab.m, d_ok);
-    c.launches += 3;
-    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_ok, ab.m, cudaMemcpyDeviceToHost, c.stream));
-    if (cc.fixed->take_error(c.stream)) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
-    if (c.time_accumulate) {
-        c.accumulate_ms += cc.fixed->last_accumulate_ms();
-        c.stat_msm_points += (uint64_t)ab.m << ab.k;
-        c.stat_msm_count += ab.m;
+    launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, nullptr, true, rs.s);
+    cc.fixed->enable_kernel_timing(rs.timing);
+    cc.fixed->run_bpoly_xyzz(d_tab, ab.m, ab.k, d_res, rs.s);
+    if (ab.curve == 0)
+        k_xyzz_equals_affine<FpParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_res, dv.d_pts_can, ab.m, d_ok);
+    else
+        k_xyzz_equals_affine<FqParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_res, dv.d_pts_can, ab.m, d_ok);
+    c.launches += 2;
+    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_ok, ab.m, cudaMemcpyDeviceToHost, rs.s));
+    if (cc.fixed->take_error(rs.s)) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
+    if (rs.timing) {
+        rs.stats.accumulate_ms += cc.fixed->last_accumulate_ms();
+        rs.stats.msm_points += (uint64_t)ab.m << ab.k;
+        rs.stats.msm_count += ab.m;
     }
     for (uint32_t i = 0; i < ab.m; i++) ab.ok[i] = h_out[i];
 }
@@ -190,7 +236,7 @@ static __global__ void __launch_bounds__(256) k_sum_slices(const fe *__restrict_
 // k_sum_slices, then ONE batched MSM (nmsm = #groups) over the resident SRS.  Commitment side: one batched
 // MSM over the batch's own points with r_j masked to zero outside each group.
 static constexpr uint32_t COMBINE_SLICE = 64;
-static std::vector<uint8_t> acc_check_groups(Context &c, SideBuffers &sb, const AccumulatorBatch &ab,
+static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab,
                                              const std::vector<std::vector<uint32_t>> &groups) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
@@ -216,87 +262,90 @@ static std::vector<uint8_t> acc_check_groups(Context &c, SideBuffers &sb, const 
         for (uint32_t j : groups[g]) std::memcpy(h_sc + 32 * ((size_t)g * ab.m + j), sb.h_r.p + 32 * (size_t)j, 32);
     uint32_t *d_meta = sb.d_subset.reserve(meta.size());
     uint32_t *d_sc = sb.d_sc.reserve((size_t)G * ab.m * 8);
-    affine *d_res = sb.d_res.reserve(2 * (size_t)G);
-    uint32_t *d_can = sb.d_out_can.reserve(32 * (size_t)G);
+    xyzz *d_res = sb.d_xyzz.reserve(2 * (size_t)G);
+    uint8_t *d_ok = reinterpret_cast<uint8_t *>(sb.d_out_can.reserve((G + 3) / 4 + 1));
     fe *d_S = sb.d_S.reserve((size_t)G << ab.k);
     const bool sliced = S != G;
     fe *d_partial = sliced ? sb.d_partial.reserve((size_t)S << ab.k) : d_S;
-    uint8_t *h_out = sb.h_out.reserve(128 * (size_t)G);
-    CTX_CUDA_OK(cudaMemcpyAsync(d_meta, h_meta, meta.size() * 4, cudaMemcpyHostToDevice, c.stream));
-    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, h_sc, (size_t)G * ab.m * 32, cudaMemcpyHostToDevice, c.stream));
-    if (c.time_accumulate) {
-        if (!c.ev_combine[0]) {
-            CTX_CUDA_OK(cudaEventCreate(&c.ev_combine[0]));
-            CTX_CUDA_OK(cudaEventCreate(&c.ev_combine[1]));
+    uint8_t *h_out = sb.h_out.reserve(G);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_meta, h_meta, meta.size() * 4, cudaMemcpyHostToDevice, rs.s));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, h_sc, (size_t)G * ab.m * 32, cudaMemcpyHostToDevice, rs.s));
+    if (rs.timing) {
+        if (!rs.ev[0]) {
+            CTX_CUDA_OK(cudaEventCreate(&rs.ev[0]));
+            CTX_CUDA_OK(cudaEventCreate(&rs.ev[1]));
         }
-        CTX_CUDA_OK(cudaEventRecord(c.ev_combine[0], c.stream));
+        CTX_CUDA_OK(cudaEventRecord(rs.ev[0], rs.s));
     }
-    launch_bpoly_combine(field, sb.d_tab.p, d_meta, d_meta + nsubset, S, nsubset, ab.k, d_partial, c.stream);
-    if (c.time_accumulate) CTX_CUDA_OK(cudaEventRecord(c.ev_combine[1], c.stream));
+    launch_bpoly_combine(field, sb.d_tab.p, d_meta, d_meta + nsubset, S, nsubset, ab.k, d_partial, rs.s);
+    if (rs.timing) CTX_CUDA_OK(cudaEventRecord(rs.ev[1], rs.s));
     c.launches += 1;
     if (sliced) {
         dim3 grid(((1u << ab.k) + 255) / 256, G);
         if (field == 0)
-            k_sum_slices<FpParams><<<grid, 256, 0, c.stream>>>(d_partial, d_meta + nsubset + S + 1, ab.k, d_S);
+            k_sum_slices<FpParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + nsubset + S + 1, ab.k, d_S);
         else
-            k_sum_slices<FqParams><<<grid, 256, 0, c.stream>>>(d_partial, d_meta + nsubset + S + 1, ab.k, d_S);
+            k_sum_slices<FqParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + nsubset + S + 1, ab.k, d_S);
         c.launches += 1;
     }
-    cc.fixed->enable_kernel_timing(c.time_accumulate);
-    cc.fixed->run(reinterpret_cast<const uint32_t *>(d_S), G, 1u << ab.k, d_res, c.stream);
-    cc.var->run(d_sc, G, ab.m, d_res + G, c.stream);
-    launch_affine_from_mont(ab.curve, d_res, d_can, 2 * G, c.stream);
+    cc.fixed->enable_kernel_timing(rs.timing);
+    cc.fixed->run_xyzz(reinterpret_cast<const uint32_t *>(d_S), G, 1u << ab.k, d_res, rs.s);
+    cc.var->run_xyzz(d_sc, G, ab.m, d_res + G, rs.s);
+    if (ab.curve == 0)
+        k_xyzz_pairs_equal<FpParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_res, d_res + G, G, d_ok);
+    else
+        k_xyzz_pairs_equal<FqParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_res, d_res + G, G, d_ok);
     c.launches += 1;
-    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_can, 128 * (size_t)G, cudaMemcpyDeviceToHost, c.stream));
-    uint32_t e = cc.fixed->take_error(c.stream) | cc.var->take_error(c.stream);  // synchronises
+    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_ok, G, cudaMemcpyDeviceToHost, rs.s));
+    uint32_t e = cc.fixed->take_error(rs.s) | cc.var->take_error(rs.s);  // synchronises
     if (e) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
-    if (c.time_accumulate) {
+    if (rs.timing) {
         float ms = 0.f;
-        CTX_CUDA_OK(cudaEventElapsedTime(&ms, c.ev_combine[0], c.ev_combine[1]));
-        c.combine_ms += ms;
-        c.accumulate_ms += cc.fixed->last_accumulate_ms();
-        c.stat_msm_points += (uint64_t)G << ab.k;
-        c.stat_msm_count += G;
-        c.stat_combine_proofs += nsubset;
-        c.stat_combine_vectors += S;
+        CTX_CUDA_OK(cudaEventElapsedTime(&ms, rs.ev[0], rs.ev[1]));
+        rs.stats.combine_ms += ms;
+        rs.stats.accumulate_ms += cc.fixed->last_accumulate_ms();
+        rs.stats.msm_points += (uint64_t)G << ab.k;
+        rs.stats.msm_count += G;
+        rs.stats.combine_proofs += nsubset;
+        rs.stats.combine_vectors += S;
     }
     std::vector<uint8_t> pass(G);
-    for (uint32_t g = 0; g < G; g++) pass[g] = std::memcmp(h_out + 64 * (size_t)g, h_out + 64 * ((size_t)G + g), 64) == 0;
+    for (uint32_t g = 0; g < G; g++) pass[g] = h_out[g];
     return pass;
 }
 
 // Group testing in levels: the whole batch first (the common case ends here: one combine + one MSM), then
 // failing groups are split ~32-ways while they are large and 8-ways below 64, every level being ONE batched
 // launch set.  A failing singleton is a bad proof: r != 0, so r*A == r*C <=> A == C.
-static void acc_rlc(Context &c, SideBuffers &sb, AccumulatorBatch &ab) {
+static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
-    AccDevice dv = acc_prepare(c, sb, ab);
+    AccDevice dv = acc_prepare(c, rs, sb, ab);
     uint8_t *h_r = sb.h_r.reserve((size_t)ab.m * 32);
     for (uint32_t i = 0; i < ab.m; i++) random_128(h_r + 32 * (size_t)i);
     fe *d_r_can = sb.d_r_can.reserve(ab.m), *d_r = sb.d_r.reserve(ab.m);
     fe *d_tab = sb.d_tab.reserve((size_t)ab.m * BPOLY_TABLE);
     affine *d_pts = sb.d_pts.reserve(ab.m);
     uint32_t *d_bad = sb.d_bad.reserve(1);
-    CTX_CUDA_OK(cudaMemcpyAsync(d_r_can, h_r, (size_t)ab.m * 32, cudaMemcpyHostToDevice, c.stream));
-    CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, c.stream));
-    launch_fe_to_mont(field, d_r_can, d_r, ab.m, c.stream);
-    launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, d_r, false, c.stream);
-    launch_affine_to_mont_checked(ab.curve, dv.d_pts_can, d_pts, ab.m, d_bad, c.stream);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_r_can, h_r, (size_t)ab.m * 32, cudaMemcpyHostToDevice, rs.s));
+    CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, rs.s));
+    launch_fe_to_mont(field, d_r_can, d_r, ab.m, rs.s);
+    launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, d_r, false, rs.s);
+    launch_affine_to_mont_checked(ab.curve, dv.d_pts_can, d_pts, ab.m, d_bad, rs.s);
     c.launches += 3;
     MsmConfig cfg;
     cfg.precompute = false;
     cfg.c = 8;
-    cc.var->set_bases(d_pts, ab.m, cfg, c.stream);
+    cc.var->set_bases(d_pts, ab.m, cfg, rs.s);
     uint32_t bad = 0;
-    CTX_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
-    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    CTX_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, rs.s));
+    CTX_CUDA_OK(cudaStreamSynchronize(rs.s));
     if (bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
     std::vector<std::vector<uint32_t>> groups(1);
     groups[0].resize(ab.m);
     for (uint32_t i = 0; i < ab.m; i++) groups[0][i] = i;
     while (!groups.empty()) {
-        std::vector<uint8_t> pass = acc_check_groups(c, sb, ab, groups);
+        std::vector<uint8_t> pass = acc_check_groups(c, rs, sb, ab, groups);
         std::vector<std::vector<uint32_t>> next;
         for (size_t g = 0; g < groups.size(); g++) {
             const std::vector<uint32_t> &grp = groups[g];
@@ -314,14 +363,52 @@ static void acc_rlc(Context &c, SideBuffers &sb, AccumulatorBatch &ab) {
     }
 }
 
-static void run_accumulators(Context &c, AccumulatorBatch &ab, int mode) {
+static void run_accumulators(Context &c, AccRun &rs, AccumulatorBatch &ab, int mode) {
     ab.ok.assign(ab.m, 0);
     if (ab.m == 0) return;
     SideBuffers &sb = vstate().side[ab.curve];
     if (mode == MINA_B200_MODE_RLC && ab.m > 1)
-        acc_rlc(c, sb, ab);
+        acc_rlc(c, rs, sb, ab);
     else
-        acc_per_proof(c, sb, ab);
+        acc_per_proof(c, rs, sb, ab);
+}
+
+// Both accumulator families of a batch, concurrently: the caller's thread drives the wrap (Vesta) side on the
+// compute stream, a helper thread drives the step (Pallas) side on the second stream.  Holds the device lock.
+static void run_both_sides(Context &c, AccumulatorBatch &wrap, AccumulatorBatch &step, int mode, bool timing,
+                           mina_b200_kernel_stats *stats_wrap, mina_b200_kernel_stats *stats_step) {
+    vstate();  // create the staging object before two threads race for it
+    AccRun rw, rp;
+    rw.s = c.stream;
+    rp.s = c.copy_stream;
+    rw.timing = rp.timing = timing;
+    std::exception_ptr err;
+    std::thread helper([&]() {
+        try {
+            if (cudaSetDevice(c.device) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed in helper thread");
+            run_accumulators(c, rp, step, mode);
+        } catch (...) {
+            err = std::current_exception();
+        }
+    });
+    try {
+        run_accumulators(c, rw, wrap, mode);
+    } catch (...) {
+        helper.join();
+        for (int i = 0; i < 2; i++) {
+            if (rw.ev[i]) cudaEventDestroy(rw.ev[i]);
+            if (rp.ev[i]) cudaEventDestroy(rp.ev[i]);
+        }
+        throw;
+    }
+    helper.join();
+    for (int i = 0; i < 2; i++) {
+        if (rw.ev[i]) cudaEventDestroy(rw.ev[i]);
+        if (rp.ev[i]) cudaEventDestroy(rp.ev[i]);
+    }
+    if (err) std::rethrow_exception(err);
+    if (stats_wrap) *stats_wrap = rw.stats;
+    if (stats_step) *stats_step = rp.stats;
 }
 
 // ---- state proofs -------------------------------------------------------------------------------------
@@ -463,8 +550,7 @@ static void verify_state_jobs(StateJob *jobs, size_t n, int mode) {
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
         CTX_CUDA_OK(cudaSetDevice(c.device));
-        run_accumulators(c, wrap, mode);
-        run_accumulators(c, step, mode);
+        run_both_sides(c, wrap, step, mode, false, nullptr, nullptr);
     }
     for (size_t t = 0; t < wrap_owner.size(); t++) {
         StateJob &j = jobs[wrap_owner[t]];
@@ -774,8 +860,7 @@ int mina_b200_accumulator_check_batch(size_t n, const unsigned char *const *proo
             Context &c = ctx();
             std::lock_guard<std::mutex> lk(c.mu);
             CTX_CUDA_OK(cudaSetDevice(c.device));
-            run_accumulators(c, wrap, mode);
-            run_accumulators(c, step, mode);
+            run_both_sides(c, wrap, step, mode, false, nullptr, nullptr);
         }
         for (size_t t = 0; t < wrap_owner.size(); t++) ok3[3 * wrap_owner[t]] = wrap.ok[t];
         for (size_t t = 0; t < step_owner.size(); t++) ok3[step_owner[t]] = step.ok[t];
@@ -805,26 +890,55 @@ int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, co
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
         CTX_CUDA_OK(cudaSetDevice(c.device));
-        c.time_accumulate = stats != nullptr;
-        c.accumulate_ms = 0.f;
-        c.combine_ms = 0.f;
-        c.stat_msm_points = c.stat_msm_count = c.stat_combine_proofs = c.stat_combine_vectors = 0;
+        AccRun rs;
+        rs.s = c.stream;
+        rs.timing = stats != nullptr;
         try {
-            run_accumulators(c, ab, mode);
+            run_accumulators(c, rs, ab, mode);
         } catch (...) {
-            c.time_accumulate = false;
+            for (int i = 0; i < 2; i++)
+                if (rs.ev[i]) cudaEventDestroy(rs.ev[i]);
             throw;
         }
-        c.time_accumulate = false;
-        if (stats) {
-            stats->accumulate_ms = c.accumulate_ms;
-            stats->combine_ms = c.combine_ms;
-            stats->msm_points = c.stat_msm_points;
-            stats->msm_count = c.stat_msm_count;
-            stats->combine_proofs = c.stat_combine_proofs;
-            stats->combine_vectors = c.stat_combine_vectors;
-        }
+        for (int i = 0; i < 2; i++)
+            if (rs.ev[i]) cudaEventDestroy(rs.ev[i]);
+        if (stats) *stats = rs.stats;
         if (m) std::memcpy(ok_host, ab.ok.data(), m);
+        return 0;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+    } catch (...) {
+        set_error("unknown error");
+    }
+    return -1;
+}
+
+// Both families of m state proofs at once (Vesta wrap accumulator + the two Pallas step accumulators per proof),
+// driven concurrently on two streams.  ok3[3*i + {0,1,2}] like mina_b200_accumulator_check_batch.
+int mina_b200_state_accumulators_device(uint32_t m, const void *d_pre_wrap, const void *d_pts_wrap, const void *d_pre_step,
+                                        const void *d_pts_step, int mode, uint8_t *ok3, mina_b200_kernel_stats *stats2) {
+    try {
+        require_ready();
+        AccumulatorBatch wrap, step;
+        wrap.curve = 1;
+        wrap.k = 16;
+        wrap.m = m;
+        wrap.d_pre_ext = (const uint8_t *)d_pre_wrap;
+        wrap.d_pts_ext = (const uint8_t *)d_pts_wrap;
+        step.curve = 0;
+        step.k = 15;
+        step.m = 2 * m;
+        step.d_pre_ext = (const uint8_t *)d_pre_step;
+        step.d_pts_ext = (const uint8_t *)d_pts_step;
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        CTX_CUDA_OK(cudaSetDevice(c.device));
+        run_both_sides(c, wrap, step, mode, stats2 != nullptr, stats2, stats2 ? stats2 + 1 : nullptr);
+        for (uint32_t i = 0; i < m; i++) {
+            ok3[3 * i] = wrap.ok[i];
+            ok3[3 * i + 1] = step.ok[2 * i];
+            ok3[3 * i + 2] = step.ok[2 * i + 1];
+        }
         return 0;
     } catch (const std::exception &e) {
         set_error(e.what());

@@ -421,3 +421,12 @@ def combined_inner_product(field: int, evals: bytes, scales: bytes, npolys: int,
     out = ctypes.create_string_buffer(32 * max(nproofs, 1))
     _check(load().mina_b200_combined_inner_product(field, ctypes.c_uint32(nproofs), ctypes.c_uint32(npolys), ctypes.c_uint32(npts), evals, scales, out))
     return out.raw[: 32 * nproofs]
+
+
+def state_accumulators_device(m: int, d_pre_w: int, d_pts_w: int, d_pre_s: int, d_pts_s: int, mode: int = MODE_RLC, want_stats: bool = False):
+    """Both accumulator families of m state proofs, the two pipelines overlapped on two streams."""
+    ok = ctypes.create_string_buffer(max(3 * m, 1))
+    st = (KernelStats * 2)()
+    _check(load().mina_b200_state_accumulators_device(ctypes.c_uint32(m), ctypes.c_void_p(d_pre_w), ctypes.c_void_p(d_pts_w),
+                                                      ctypes.c_void_p(d_pre_s), ctypes.c_void_p(d_pts_s), mode, ok, st if want_stats else None))
+    return (ok.raw[: 3 * m], (st[0], st[1])) if want_stats else ok.raw[: 3 * m]

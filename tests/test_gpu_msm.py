@@ -54,6 +54,8 @@ def test_both_device_multipliers_match_the_portable_product(gpu):
         assert gpu.field_op(fid, 16, A, B) == want
         assert gpu.field_op(fid, 17, A, B) == want
         assert gpu.field_op(fid, 10, A, B) == want
+        # dedicated squaring (op 4 converts in and out of Montgomery form around Fd::sqr)
+        assert gpu.field_op(fid, 4, A) == cref.ints_to_bytes([x * x % m for x in a])
 
 
 def test_device_srs_is_the_reference_srs(gpu):
