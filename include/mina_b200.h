@@ -211,6 +211,14 @@ int mina_b200_host_vk_load(const char *path, uint8_t *out, uint32_t meta[4]);
 /* Host Poseidon sponge: hash_with_kimchi(prefix, xs[0..n)) with the given table (Fp). */
 int mina_b200_host_hash_with_kimchi(const uint8_t *table, const char *prefix, const uint8_t *xs32, uint32_t n, uint8_t out32[32]);
 int mina_b200_host_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96);
+/* Wire encoders (csrc/wire_write.hpp; the producer side, core/src/aligned.rs:33-49): decode `data` as `kind`
+ * (same ids as mina_b200_host_decode) and encode it again.  *out_len in = capacity, out = bytes written.
+ * Returns 0, -1 decode error, -2 not re-encodable / buffer too small. */
+int mina_b200_host_reencode(int kind, const uint8_t *data, size_t len, uint8_t *out, size_t *out_len);
+/* Solidity ABI encoding of the account inside an account proof (core/src/sol/account.rs:25-314 +
+ * `abi_encode()`, mina_account lib.rs:54-62): what the verifier compares with the public input's
+ * `encoded_account`.  Returns 0, -1 decode error, -2 conversion failure (non-UTF-8 token symbol) / buffer too small. */
+int mina_b200_host_account_abi_encode(const uint8_t *account_proof, size_t len, uint8_t *out, size_t *out_len);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,9 @@
 #include "../../include/mina_b200.h"
 #include "consensus.hpp"
 #include "context.cuh"
+#include "sol_account.hpp"
 #include "wire.hpp"
+#include "wire_write.hpp"
 
 using namespace pasta;
 
@@ -295,6 +297,60 @@ int mina_b200_host_hash_with_kimchi(const uint8_t *table, const char *prefix, co
     if (!poseidon::hash_with_kimchi<FpParams>(params, prefix, xs.data(), n, out)) return -3;
     out.to_bytes_le(out32);
     return 0;
+}
+
+static int emit_bytes(const std::vector<uint8_t> &enc, uint8_t *out, size_t *out_len) {
+    if (!out_len || enc.size() > *out_len) {
+        set_error("output buffer too small");
+        return -2;
+    }
+    if (!enc.empty()) std::memcpy(out, enc.data(), enc.size());
+    *out_len = enc.size();
+    return 0;
+}
+
+int mina_b200_host_reencode(int kind, const uint8_t *data, size_t len, uint8_t *out, size_t *out_len) {
+    try {
+        std::string err;
+        std::vector<uint8_t> enc;
+        if (kind == 0) {
+            auto p = std::make_unique<wire::StateProof>();
+            if (!wire::decode_state_proof(data, len, *p, err)) return set_error(err), -1;
+            if (!wire::encode_state_proof(*p, enc)) return set_error("proof carries optional evaluations"), -2;
+        } else if (kind == 1) {
+            wire::StatePubInputs pub;
+            if (!wire::decode_state_pub(data, len, pub, err)) return set_error(err), -1;
+            wire::encode_state_pub(pub, enc);
+        } else if (kind == 2) {
+            wire::AccountProof ap;
+            if (!wire::decode_account_proof(data, len, ap, err)) return set_error(err), -1;
+            wire::encode_account_proof(ap, enc);
+        } else if (kind == 3) {
+            wire::AccountPubInputs pub;
+            if (!wire::decode_account_pub(data, len, pub, err)) return set_error(err), -1;
+            wire::encode_account_pub(pub, enc);
+        } else {
+            return set_error("bad kind"), -1;
+        }
+        return emit_bytes(enc, out, out_len);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return -1;
+    }
+}
+
+int mina_b200_host_account_abi_encode(const uint8_t *account_proof, size_t len, uint8_t *out, size_t *out_len) {
+    try {
+        std::string err;
+        wire::AccountProof ap;
+        if (!wire::decode_account_proof(account_proof, len, ap, err)) return set_error(err), -1;
+        std::vector<uint8_t> enc;
+        if (!sol::abi_encode_account(ap.account, enc)) return set_error("token symbol is not UTF-8"), -2;
+        return emit_bytes(enc, out, out_len);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return -1;
+    }
 }
 
 int mina_b200_host_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96) {

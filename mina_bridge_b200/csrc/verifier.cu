@@ -32,6 +32,7 @@
 #include "context.cuh"
 #include "ipa.cuh"
 #include "poseidon.cuh"
+#include "sol_account.hpp"
 #include "wire.hpp"
 
 namespace pasta {
@@ -591,10 +592,16 @@ static void account_host_pass(AccountJob &j) {
     pass(MINA_B200_STAGE_DECODE_PROOF);
     if (!wire::decode_account_pub(j.pub, j.pub_len, pub, err) || !canonical<FpParams>(pub.ledger_hash, tmp)) return fail(MINA_B200_STAGE_DECODE_PUB);
     pass(MINA_B200_STAGE_DECODE_PUB);
-    // mina_account/lib/src/lib.rs:54-66 (Solidity ABI re-encoding, core/src/sol/account.rs) and :70
-    // (Account::hash) are SURVEY 8f-3 "next" rows: not built.  The Merkle fold (merkle_verifier.rs:9-35)
-    // exists as a kernel (k_merkle_fold) but needs the leaf hash and a trusted Poseidon table.
-    unavailable(MINA_B200_STAGE_ACCOUNT_ABI);
+    // mina_account/lib/src/lib.rs:54-66: the Solidity ABI encoding of the proof's account must equal the
+    // public input's `encoded_account` byte for byte (conversion failure -> reject)
+    {
+        std::vector<uint8_t> expected;
+        if (!sol::abi_encode_account(proof.account, expected) || expected != pub.encoded_account) return fail(MINA_B200_STAGE_ACCOUNT_ABI);
+        pass(MINA_B200_STAGE_ACCOUNT_ABI);
+    }
+    // :70 Account::hash (mina-tree ROInput packing + Poseidon, un-vendored) is not built.  The Merkle fold
+    // (merkle_verifier.rs:9-35) exists as a kernel (k_merkle_fold) but needs the leaf hash and a trusted
+    // Poseidon table.
     unavailable(MINA_B200_STAGE_ACCOUNT_LEAF);
     unavailable(MINA_B200_STAGE_MERKLE);
 }

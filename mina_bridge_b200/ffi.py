@@ -322,6 +322,28 @@ def host_decode(kind: int, data: bytes):
     return s if rc == 0 else None
 
 
+def _host_bytes_out(fn, *args, cap=1 << 17):
+    buf = ctypes.create_string_buffer(cap)
+    n = ctypes.c_size_t(cap)
+    rc = fn(*args, buf, ctypes.byref(n))
+    return (buf.raw[:n.value] if rc == 0 else None), rc
+
+
+def host_reencode(kind: int, data: bytes):
+    """decode + encode through the C++ wire writers (csrc/wire_write.hpp).  None on a decode error."""
+    lib = load()
+    lib.mina_b200_host_reencode.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    return _host_bytes_out(lib.mina_b200_host_reencode, kind, data, len(data))[0]
+
+
+def host_account_abi_encode(account_proof: bytes):
+    """Solidity ABI encoding of the account inside an account proof (the verifier's expected_encoded_account).
+    None when the proof does not decode or the conversion fails like the reference's TryFrom."""
+    lib = load()
+    lib.mina_b200_host_account_abi_encode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    return _host_bytes_out(lib.mina_b200_host_account_abi_encode, account_proof, len(account_proof))[0]
+
+
 def host_select_secure_chain(candidate: bytes, tip: bytes) -> int:
     """1 = Candidate, 0 = Bridge; raises on the reference's Err / undecodable input."""
     res = ctypes.c_int(-1)

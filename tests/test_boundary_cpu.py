@@ -113,8 +113,105 @@ def test_valid_vectors_are_never_accepted_on_a_partial_check(mb):
     assert rep.failed & ~S["internal_error"] == 0  # internal_error only when there is no device (this tier)
     assert mb.verify_account_inclusion(golden("mina_account.proof"), golden("mina_account.pub")) is False
     rep = mb.last_stages()
-    assert rep.failed == 0 and rep.unavailable == S["account_abi"] | S["account_leaf"] | S["merkle"]
-    assert rep.passed == S["lengths"] | S["decode_proof"] | S["decode_pub"]
+    assert rep.failed == 0 and rep.unavailable == S["account_leaf"] | S["merkle"]
+    assert rep.passed == S["lengths"] | S["decode_proof"] | S["decode_pub"] | S["account_abi"]
+
+
+# ---- account ABI re-encoding (mina_account lib.rs:54-66, core/src/sol/account.rs) ---------------------------------
+def test_account_abi_encoding_matches_the_fixture(mb):
+    """The reference rejects unless abi_encode(Account::try_from(&proof.account)) == pub.encoded_account; its own
+    fixture pair therefore pins the encoder: 3 456 bytes, identical."""
+    enc = mb.host_account_abi_encode(golden("mina_account.proof"))
+    assert enc is not None and len(enc) == 3456
+    assert enc == golden("mina_account.pub")[40:]
+
+
+def _account_fields():
+    """byte offsets inside mina_account.proof: the account starts at 1 548"""
+    a = 1548
+    return {"public_key_x": a + 8, "is_odd": a + 40, "token_id": a + 49, "symbol_len": a + 81, "balance": a + 89,
+            "nonce": a + 97, "receipt": a + 109, "delegate_tag": a + 141, "delegate_x": a + 150, "voting_for": a + 191,
+            "timing_tag": a + 223, "perm0": a + 227, "zkapp_tag": a + 283}
+
+
+def test_account_abi_stage_rejects_a_mismatch(mb):
+    """one flipped byte in any account field of the proof, or in the encoded account of the public input, fails
+    the ABI stage (and nothing else) -- the reference's `expected_encoded_account != encoded_account` branch"""
+    p, q = golden("mina_account.proof"), golden("mina_account.pub")
+    f = _account_fields()
+    for name in ("public_key_x", "token_id", "balance", "nonce", "receipt", "delegate_x", "voting_for"):
+        m = bytearray(p)
+        m[f[name]] ^= 1
+        assert mb.verify_account_inclusion(bytes(m), q) is False
+        rep = mb.last_stages()
+        assert rep.failed == S["account_abi"], name
+    for off in (40 + 32 + 5, 40 + 5 * 32 + 31, len(q) - 1):
+        m = bytearray(q)
+        m[off] ^= 1
+        assert mb.verify_account_inclusion(p, bytes(m)) is False
+        assert mb.last_stages().failed == S["account_abi"]
+
+
+def test_account_abi_encoding_of_variants(mb):
+    """Branches the fixture does not take (account.rs:57-69, 73-110), checked against a Python restatement of the
+    Solidity ABI rules: no delegate -> (0, isOdd = true); a timed account; a non-empty token symbol (dynamic tail
+    grows, zkapp offset moves); permissions other than Signature."""
+    p = bytearray(golden("mina_account.proof"))
+    f = _account_fields()
+    base = mb.host_account_abi_encode(bytes(p))
+    word = lambda v: v.to_bytes(32, "big")
+    # (a) delegate = None: drop the 41-byte public key
+    m = bytes(p[:f["delegate_tag"]]) + b"\0" + bytes(p[f["delegate_tag"] + 42:])
+    enc = mb.host_account_abi_encode(m)
+    want = bytearray(base)
+    want[32 * 8:32 * 9] = b"\0" * 32
+    want[32 * 9:32 * 10] = word(1)
+    assert enc == bytes(want)
+    # (b) timed account
+    timed = (1).to_bytes(4, "little") + (1000).to_bytes(8, "little") + (7).to_bytes(4, "little") + (11).to_bytes(8, "little") + \
+        (13).to_bytes(4, "little") + (17).to_bytes(8, "little")
+    m = bytes(p[:f["timing_tag"]]) + timed + bytes(p[f["timing_tag"] + 4:])
+    enc = mb.host_account_abi_encode(m)
+    want = bytearray(base)
+    for i, v in enumerate((1000, 7, 11, 13, 17)):
+        want[32 * (11 + i):32 * (12 + i)] = word(v)
+    assert enc == bytes(want)
+    # (c) token symbol "MINA": the string tail gains one data word and the zkapp offset moves by 32
+    m = bytes(p[:f["symbol_len"]]) + (4).to_bytes(8, "little") + b"MINA" + bytes(p[f["symbol_len"] + 8:])
+    enc = mb.host_account_abi_encode(m)
+    want = bytes(base[:32 * 30]) + word(0x3e0 + 32) + word(4) + b"MINA" + b"\0" * 28 + bytes(base[32 * 32:])
+    assert enc == want
+    # ... and one that is not UTF-8 is a conversion failure
+    m = bytes(p[:f["symbol_len"]]) + (2).to_bytes(8, "little") + b"\xff\xfe" + bytes(p[f["symbol_len"] + 8:])
+    assert mb.host_account_abi_encode(m) is None
+    # (d) permissions: edit_state = Impossible (tag 4)
+    m = bytearray(p)
+    m[f["perm0"]:f["perm0"] + 4] = (4).to_bytes(4, "little")
+    enc = mb.host_account_abi_encode(bytes(m))
+    want = bytearray(base)
+    want[32 * 16:32 * 17] = word(4)
+    assert enc == bytes(want)
+
+
+# ---- wire writers (SURVEY 8f-4: core/src/aligned.rs:33-49) ---------------------------------------------------
+@pytest.mark.parametrize("kind,name", [(0, "mina_state.proof"), (1, "mina_state.pub"), (1, "mina_state_bad_hash.pub"),
+                                       (2, "mina_account.proof"), (3, "mina_account.pub")])
+def test_writers_reproduce_the_fixtures(mb, kind, name):
+    """decode -> encode through the C++ writers gives back the reference's committed bytes exactly"""
+    data = golden(name)
+    if name == "mina_state_bad_hash.pub":
+        assert mb.host_reencode(kind, data) is None  # first byte 0x5d is not a bool (SURVEY Q10)
+        return
+    assert mb.host_reencode(kind, data) == data
+
+
+def test_writers_round_trip_mutated_proofs(mb):
+    """the writers are what synthetic batches are made of: mutate -> encode -> decode must be stable"""
+    data = bytearray(golden("mina_state.proof"))
+    for off in (80, 380, 5000, 14000, 30000):
+        data[off] ^= 0x10
+        enc = mb.host_reencode(0, bytes(data))
+        assert enc == bytes(data)
 
 
 def test_concurrent_callers_do_not_deadlock(mb):
