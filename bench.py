@@ -256,6 +256,14 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
     t_pp_e2e, _ = timed(lambda: step_e2e(mb.MODE_PER_PROOF), pp_steps)
     sampler.stop.set()
     sampler.join()
+    if a.profile_step:
+        # one extra step inside a cudaProfilerStart/Stop range, outside every timed region: what the committed
+        # ncu passes capture (`ncu --profile-from-start off ...`, profiles/README in DESIGN.md section 4)
+        barrier()
+        torch.cuda.profiler.start()
+        step_device(mb.MODE_PER_PROOF if a.profile_step == "per_proof" else mb.MODE_RLC)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if rank != 0:
         return None
     peak, which = peaks()
@@ -406,6 +414,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20"])
+    ap.add_argument("--profile-step", default="", choices=["", "rlc", "per_proof"],
+                    help="run one extra untimed step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off)")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)

@@ -148,6 +148,10 @@ static void destroy_device_state(Context &c) {
     }
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    for (cudaStream_t &a : c.aux_stream) {
+        if (a) cudaStreamDestroy(a);
+        a = nullptr;
+    }
     c.stream = c.copy_stream = nullptr;
     c.ready = false;
     c.device = -1;
@@ -212,6 +216,7 @@ int mina_b200_init(int device, const char *data_dir) {
         c.data_dir = (data_dir && *data_dir) ? std::string(data_dir) : default_data_dir();
         CTX_CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         CTX_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        for (cudaStream_t &a : c.aux_stream) CTX_CUDA_OK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
         // Both files in the reference hold 65536 points; the Pallas side only ever uses the first 2^15.
         c.srs_vesta = load_or_create_srs<FqParams>(c.data_dir, "vesta", VESTA_SRS_DEPTH);
         c.srs_pallas = load_or_create_srs<FpParams>(c.data_dir, "pallas", PALLAS_SRS_DEPTH);

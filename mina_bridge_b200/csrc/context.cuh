@@ -100,6 +100,7 @@ struct Context {
     bool ready = false;
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t copy_stream = nullptr;  // H2D staging that overlaps compute; second pipeline of a state batch
+    cudaStream_t aux_stream[2] = {nullptr, nullptr};  // per pipeline: work that runs beside the MSM (r_j * C_j)
     CurveCtx curve[2];
     host::Srs<FpParams> srs_pallas;  // coordinates in Fp
     host::Srs<FqParams> srs_vesta;   // coordinates in Fq

@@ -40,12 +40,12 @@ namespace pasta {
 // ---- persistent staging ---------------------------------------------------------------------------
 struct SideBuffers {  // one accumulator family (Vesta k=16 or Pallas k=15)
     PinnedBuf<uint8_t> h_pre, h_pts, h_r, h_out;
-    PinnedBuf<uint32_t> h_subset;
+    PinnedBuf<uint32_t> h_subset, h_bad;
     DevBuf<uint8_t> d_pre;
     DevBuf<fe> d_chal, d_r_can, d_r, d_tab, d_S, d_partial;
     DevBuf<uint32_t> d_subset, d_pts_can, d_out_can, d_bad, d_sc;
     DevBuf<affine> d_pts, d_res;
-    DevBuf<xyzz> d_xyzz;
+    DevBuf<xyzz> d_xyzz, d_scaled;
 };
 struct VerifierState {
     SideBuffers side[2];  // index = curve id: 0 Pallas (step accumulators), 1 Vesta (wrap accumulator)
@@ -55,6 +55,12 @@ struct VerifierState {
     DevBuf<fe> d_leaves, d_roots, d_prefix, d_folded;
     DevBuf<uint8_t> d_ok;
     uint32_t prefix_depth = 0;
+    cudaEvent_t fork_join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // per pipeline: fork, join (timing disabled)
+    ~VerifierState() {
+        for (auto &pair : fork_join)
+            for (cudaEvent_t &e : pair)
+                if (e) cudaEventDestroy(e);
+    }
 };
 void verifier_release(Context &c) {
     delete c.verifier;
@@ -160,7 +166,9 @@ static __global__ void __launch_bounds__(128) k_xyzz_pairs_equal(const xyzz *__r
 // pipelines of a batch can be driven by two host threads and overlap on the device (their MSM tails are
 // latency-bound and leave most SMs idle).
 struct AccRun {
-    cudaStream_t s = nullptr;
+    cudaStream_t s = nullptr, aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;  // owned by VerifierState (created once)
+    cudaEvent_t scaled_ready = nullptr;          // set while the P_j of this batch are still in flight on `aux`
     bool timing = false;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     mina_b200_kernel_stats stats{0.f, 0.f, 0, 0, 0, 0};
@@ -170,6 +178,18 @@ struct AccDevice {  // device views of one prepared batch
     const uint8_t *d_pre = nullptr;
     const uint32_t *d_pts_can = nullptr;
 };
+
+// pipeline 0 = the caller's thread on the compute stream, 1 = the helper thread on the second stream
+static void setup_run(Context &c, AccRun &rs, int pipeline, bool timing) {
+    VerifierState &vs = vstate();
+    for (cudaEvent_t &e : vs.fork_join[pipeline])
+        if (!e) CTX_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    rs.s = pipeline == 0 ? c.stream : c.copy_stream;
+    rs.aux = c.aux_stream[pipeline];
+    rs.fork = vs.fork_join[pipeline][0];
+    rs.join = vs.fork_join[pipeline][1];
+    rs.timing = timing;
+}
 
 static AccDevice acc_prepare(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;  // scalar field of the curve
@@ -231,46 +251,148 @@ static __global__ void __launch_bounds__(256) k_sum_slices(const fe *__restrict_
     out[((size_t)blockIdx.y << k) + i] = acc;
 }
 
+// ---- commitment side of the random linear combination ----------------------------------------------
+// P_j = r_j * C_j once per batch (r_j < 2^128: plain double-and-add, one thread per point, left in XYZZ).
+// It runs on the pipeline's auxiliary stream beside the table / combine / MSM work of level 0; every
+// level then only needs sums of P_j over its groups (k_subset_sums), not another MSM.
+template <class F>
+static __global__ void __launch_bounds__(64) k_scale_points_128(const affine *__restrict__ pts, const fe *__restrict__ r_can, uint32_t m,
+                                                                xyzz *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const affine q = pts[i];
+    const fe r = r_can[i];
+    xyzz acc = Ec<F>::identity();
+#pragma unroll 1
+    for (int b = 127; b >= 0; b--) {
+        acc = Ec<F>::dbl(acc);
+        if ((r.v[b >> 5] >> (b & 31)) & 1u) Ec<F>::add_mixed(acc, q);
+    }
+    out[i] = acc;
+}
+template <class F>
+static __device__ __forceinline__ xyzz shfl_down_xyzz(const xyzz &p, int delta) {
+    xyzz r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], delta);
+        r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], delta);
+        r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], delta);
+        r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], delta);
+    }
+    return r;
+}
+// block-wide sum of one XYZZ point per thread (result valid in thread 0)
+static constexpr int SUBSET_THREADS = 128;
+template <class F>
+static __device__ __forceinline__ xyzz block_sum_xyzz(xyzz acc, xyzz *warp_part) {
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        xyzz o = shfl_down_xyzz<F>(acc, d);
+        Ec<F>::add(acc, o);
+    }
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_part[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        acc = lane < SUBSET_THREADS / 32 ? warp_part[lane] : Ec<F>::identity();
+#pragma unroll 1
+        for (int d = SUBSET_THREADS / 64; d >= 1; d >>= 1) {
+            xyzz o = shfl_down_xyzz<F>(acc, d);
+            Ec<F>::add(acc, o);
+        }
+    }
+    return acc;
+}
+// D[g] = sum_{t in [goff[g], goff[g+1])} P[subset[t]]: one block per group
+template <class F>
+static __global__ void __launch_bounds__(SUBSET_THREADS) k_subset_sums(const xyzz *__restrict__ P, const uint32_t *__restrict__ subset,
+                                                                       const uint32_t *__restrict__ goff, xyzz *__restrict__ out) {
+    __shared__ xyzz warp_part[SUBSET_THREADS / 32];
+    const uint32_t t0 = goff[blockIdx.x], t1 = goff[blockIdx.x + 1];
+    xyzz acc = Ec<F>::identity();
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += SUBSET_THREADS) Ec<F>::add(acc, P[subset[t]]);
+    acc = block_sum_xyzz<F>(acc, warp_part);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+// The last child of every split group needs no MSM:  A_last = A_parent - sum of its siblings' A.
+// derived[3*d + {0,1,2}] = parent index in `A_prev`, [sib_begin, sib_end) in `A` (this level's MSM results);
+// the result goes to A[n_msm + d].  One block per derived group.
+template <class F>
+static __global__ void __launch_bounds__(SUBSET_THREADS) k_derive_last_child(const xyzz *__restrict__ A_prev, xyzz *__restrict__ A,
+                                                                             const uint32_t *__restrict__ derived, uint32_t n_msm) {
+    __shared__ xyzz warp_part[SUBSET_THREADS / 32];
+    const uint32_t parent = derived[3 * blockIdx.x], s0 = derived[3 * blockIdx.x + 1], s1 = derived[3 * blockIdx.x + 2];
+    xyzz acc = Ec<F>::identity();
+    for (uint32_t t = s0 + threadIdx.x; t < s1; t += SUBSET_THREADS) Ec<F>::add(acc, A[t]);
+    acc = block_sum_xyzz<F>(acc, warp_part);
+    if (threadIdx.x == 0) {
+        acc.y = Fd<F>::neg(acc.y);
+        xyzz p = A_prev[parent];
+        Ec<F>::add(p, acc);
+        A[n_msm + blockIdx.x] = p;
+    }
+}
+
+// One level of the group testing.  Groups that need an MSM come first, then the "derived" ones (last child
+// of each split parent, obtained by subtraction).
+struct LevelGroup {
+    std::vector<uint32_t> members;
+    uint32_t parent = 0;          // index into the previous level's group list
+    bool derived = false;
+};
+struct LevelPlan {
+    std::vector<LevelGroup> msm, derived;
+    std::vector<std::array<uint32_t, 3>> derived_meta;  // parent, sibling range among `msm`
+    size_t size() const { return msm.size() + derived.size(); }
+    const LevelGroup &at(size_t g) const { return g < msm.size() ? msm[g] : derived[g - msm.size()]; }
+};
+
 // One level of random-linear-combination checks, ALL groups in one launch set:
 //   pass[g]  <=>  < sum_{j in g} r_j b_poly_coefficients(chals_j), G >  ==  sum_{j in g} r_j C_j.
 // g side: k_bpoly_combine over slices of <= 64 proofs (so a single large group still fills the GPU),
-// k_sum_slices, then ONE batched MSM (nmsm = #groups) over the resident SRS.  Commitment side: one batched
-// MSM over the batch's own points with r_j masked to zero outside each group.
+// k_sum_slices, then ONE batched MSM (nmsm = #groups that need one) over the resident SRS; derived groups
+// by subtraction.  Commitment side: sums of the precomputed P_j = r_j C_j.
 static constexpr uint32_t COMBINE_SLICE = 64;
-static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab,
-                                             const std::vector<std::vector<uint32_t>> &groups) {
+static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab, const LevelPlan &plan,
+                                             int parity) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
-    const uint32_t G = (uint32_t)groups.size();
-    std::vector<uint32_t> meta;  // subset | slice_off | group_slice_off, one upload
-    std::vector<uint32_t> slice_off{0}, gso{0};
-    for (auto &g : groups) {
-        for (size_t at = 0; at < g.size(); at += COMBINE_SLICE) {
-            size_t end = std::min(g.size(), at + COMBINE_SLICE);
-            meta.insert(meta.end(), g.begin() + at, g.begin() + end);
-            slice_off.push_back((uint32_t)meta.size());
+    const uint32_t Gm = (uint32_t)plan.msm.size(), Gd = (uint32_t)plan.derived.size(), G = Gm + Gd;
+    // one upload: subset (all groups) | slice_off (MSM groups) | gso (MSM groups) | goff (all groups) | derived triples
+    std::vector<uint32_t> meta, slice_off{0}, gso{0}, goff{0};
+    for (uint32_t g = 0; g < G; g++) {
+        const std::vector<uint32_t> &mem = plan.at(g).members;
+        if (g < Gm) {
+            for (size_t at = 0; at < mem.size(); at += COMBINE_SLICE)
+                slice_off.push_back((uint32_t)(meta.size() + std::min(mem.size(), at + COMBINE_SLICE)));
+            gso.push_back((uint32_t)slice_off.size() - 1);
         }
-        gso.push_back((uint32_t)slice_off.size() - 1);
+        meta.insert(meta.end(), mem.begin(), mem.end());
+        goff.push_back((uint32_t)meta.size());
     }
-    const uint32_t nsubset = (uint32_t)meta.size(), S = (uint32_t)slice_off.size() - 1;
+    const uint32_t nsub_all = (uint32_t)meta.size(), nsub_msm = slice_off.back(), S = (uint32_t)slice_off.size() - 1;
+    const size_t o_slice = meta.size();
     meta.insert(meta.end(), slice_off.begin(), slice_off.end());
+    const size_t o_gso = meta.size();
     meta.insert(meta.end(), gso.begin(), gso.end());
+    const size_t o_goff = meta.size();
+    meta.insert(meta.end(), goff.begin(), goff.end());
+    const size_t o_der = meta.size();
+    for (auto &d : plan.derived_meta) meta.insert(meta.end(), d.begin(), d.end());
+    (void)nsub_all;
     uint32_t *h_meta = sb.h_subset.reserve(meta.size());
     std::memcpy(h_meta, meta.data(), meta.size() * 4);
-    uint8_t *h_sc = sb.h_pts.reserve((size_t)G * ab.m * 32);
-    std::memset(h_sc, 0, (size_t)G * ab.m * 32);
-    for (uint32_t g = 0; g < G; g++)
-        for (uint32_t j : groups[g]) std::memcpy(h_sc + 32 * ((size_t)g * ab.m + j), sb.h_r.p + 32 * (size_t)j, 32);
     uint32_t *d_meta = sb.d_subset.reserve(meta.size());
-    uint32_t *d_sc = sb.d_sc.reserve((size_t)G * ab.m * 8);
-    xyzz *d_res = sb.d_xyzz.reserve(2 * (size_t)G);
+    // XYZZ scratch: [A even | A odd | D], each ab.m long (groups are disjoint and non-empty: G <= m)
+    xyzz *d_x = sb.d_xyzz.reserve(3 * (size_t)ab.m);
+    xyzz *d_A = d_x + (size_t)(parity & 1) * ab.m, *d_A_prev = d_x + (size_t)((parity & 1) ^ 1) * ab.m, *d_D = d_x + 2 * (size_t)ab.m;
     uint8_t *d_ok = reinterpret_cast<uint8_t *>(sb.d_out_can.reserve((G + 3) / 4 + 1));
-    fe *d_S = sb.d_S.reserve((size_t)G << ab.k);
-    const bool sliced = S != G;
+    fe *d_S = sb.d_S.reserve((size_t)Gm << ab.k);
+    const bool sliced = S != Gm;
     fe *d_partial = sliced ? sb.d_partial.reserve((size_t)S << ab.k) : d_S;
     uint8_t *h_out = sb.h_out.reserve(G);
     CTX_CUDA_OK(cudaMemcpyAsync(d_meta, h_meta, meta.size() * 4, cudaMemcpyHostToDevice, rs.s));
-    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, h_sc, (size_t)G * ab.m * 32, cudaMemcpyHostToDevice, rs.s));
     if (rs.timing) {
         if (!rs.ev[0]) {
             CTX_CUDA_OK(cudaEventCreate(&rs.ev[0]));
@@ -278,36 +400,44 @@ static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers
         }
         CTX_CUDA_OK(cudaEventRecord(rs.ev[0], rs.s));
     }
-    launch_bpoly_combine(field, sb.d_tab.p, d_meta, d_meta + nsubset, S, nsubset, ab.k, d_partial, rs.s);
+    launch_bpoly_combine(field, sb.d_tab.p, d_meta, d_meta + o_slice, S, nsub_msm, ab.k, d_partial, rs.s);
     if (rs.timing) CTX_CUDA_OK(cudaEventRecord(rs.ev[1], rs.s));
     c.launches += 1;
     if (sliced) {
-        dim3 grid(((1u << ab.k) + 255) / 256, G);
+        dim3 grid(((1u << ab.k) + 255) / 256, Gm);
         if (field == 0)
-            k_sum_slices<FpParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + nsubset + S + 1, ab.k, d_S);
+            k_sum_slices<FpParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + o_gso, ab.k, d_S);
         else
-            k_sum_slices<FqParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + nsubset + S + 1, ab.k, d_S);
+            k_sum_slices<FqParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + o_gso, ab.k, d_S);
         c.launches += 1;
     }
     cc.fixed->enable_kernel_timing(rs.timing);
-    cc.fixed->run_xyzz(reinterpret_cast<const uint32_t *>(d_S), G, 1u << ab.k, d_res, rs.s);
-    cc.var->run_xyzz(d_sc, G, ab.m, d_res + G, rs.s);
-    if (ab.curve == 0)
-        k_xyzz_pairs_equal<FpParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_res, d_res + G, G, d_ok);
-    else
-        k_xyzz_pairs_equal<FqParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_res, d_res + G, G, d_ok);
-    c.launches += 1;
+    cc.fixed->run_xyzz(reinterpret_cast<const uint32_t *>(d_S), Gm, 1u << ab.k, d_A, rs.s);
+    if (rs.scaled_ready) {  // first level: the P_j come from the auxiliary stream
+        CTX_CUDA_OK(cudaStreamWaitEvent(rs.s, rs.scaled_ready, 0));
+        rs.scaled_ready = nullptr;
+    }
+    if (ab.curve == 0) {
+        k_subset_sums<FpParams><<<G, SUBSET_THREADS, 0, rs.s>>>(sb.d_scaled.p, d_meta, d_meta + o_goff, d_D);
+        if (Gd) k_derive_last_child<FpParams><<<Gd, SUBSET_THREADS, 0, rs.s>>>(d_A_prev, d_A, d_meta + o_der, Gm);
+        k_xyzz_pairs_equal<FpParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_A, d_D, G, d_ok);
+    } else {
+        k_subset_sums<FqParams><<<G, SUBSET_THREADS, 0, rs.s>>>(sb.d_scaled.p, d_meta, d_meta + o_goff, d_D);
+        if (Gd) k_derive_last_child<FqParams><<<Gd, SUBSET_THREADS, 0, rs.s>>>(d_A_prev, d_A, d_meta + o_der, Gm);
+        k_xyzz_pairs_equal<FqParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_A, d_D, G, d_ok);
+    }
+    c.launches += Gd ? 3 : 2;
     CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_ok, G, cudaMemcpyDeviceToHost, rs.s));
-    uint32_t e = cc.fixed->take_error(rs.s) | cc.var->take_error(rs.s);  // synchronises
+    uint32_t e = cc.fixed->take_error(rs.s);  // synchronises
     if (e) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
     if (rs.timing) {
         float ms = 0.f;
         CTX_CUDA_OK(cudaEventElapsedTime(&ms, rs.ev[0], rs.ev[1]));
         rs.stats.combine_ms += ms;
         rs.stats.accumulate_ms += cc.fixed->last_accumulate_ms();
-        rs.stats.msm_points += (uint64_t)G << ab.k;
-        rs.stats.msm_count += G;
-        rs.stats.combine_proofs += nsubset;
+        rs.stats.msm_points += (uint64_t)Gm << ab.k;
+        rs.stats.msm_count += Gm;
+        rs.stats.combine_proofs += nsub_msm;
         rs.stats.combine_vectors += S;
     }
     std::vector<uint8_t> pass(G);
@@ -320,47 +450,67 @@ static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers
 // launch set.  A failing singleton is a bad proof: r != 0, so r*A == r*C <=> A == C.
 static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;
-    CurveCtx &cc = c.curve[ab.curve];
     AccDevice dv = acc_prepare(c, rs, sb, ab);
     uint8_t *h_r = sb.h_r.reserve((size_t)ab.m * 32);
     for (uint32_t i = 0; i < ab.m; i++) random_128(h_r + 32 * (size_t)i);
     fe *d_r_can = sb.d_r_can.reserve(ab.m), *d_r = sb.d_r.reserve(ab.m);
     fe *d_tab = sb.d_tab.reserve((size_t)ab.m * BPOLY_TABLE);
     affine *d_pts = sb.d_pts.reserve(ab.m);
+    xyzz *d_scaled = sb.d_scaled.reserve(ab.m);
     uint32_t *d_bad = sb.d_bad.reserve(1);
+    uint32_t *h_bad = sb.h_bad.reserve(1);
     CTX_CUDA_OK(cudaMemcpyAsync(d_r_can, h_r, (size_t)ab.m * 32, cudaMemcpyHostToDevice, rs.s));
     CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, rs.s));
+    launch_affine_to_mont_checked(ab.curve, dv.d_pts_can, d_pts, ab.m, d_bad, rs.s);
+    CTX_CUDA_OK(cudaMemcpyAsync(h_bad, d_bad, 4, cudaMemcpyDeviceToHost, rs.s));
+    // P_j = r_j C_j beside the rest of level 0
+    CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));
+    CTX_CUDA_OK(cudaStreamWaitEvent(rs.aux, rs.fork, 0));
+    if (ab.curve == 0)
+        k_scale_points_128<FpParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(d_pts, d_r_can, ab.m, d_scaled);
+    else
+        k_scale_points_128<FqParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(d_pts, d_r_can, ab.m, d_scaled);
+    CTX_CUDA_OK(cudaEventRecord(rs.join, rs.aux));
+    rs.scaled_ready = rs.join;
     launch_fe_to_mont(field, d_r_can, d_r, ab.m, rs.s);
     launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, d_r, false, rs.s);
-    launch_affine_to_mont_checked(ab.curve, dv.d_pts_can, d_pts, ab.m, d_bad, rs.s);
-    c.launches += 3;
-    MsmConfig cfg;
-    cfg.precompute = false;
-    cfg.c = 8;
-    cc.var->set_bases(d_pts, ab.m, cfg, rs.s);
-    uint32_t bad = 0;
-    CTX_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, rs.s));
-    CTX_CUDA_OK(cudaStreamSynchronize(rs.s));
-    if (bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
-    std::vector<std::vector<uint32_t>> groups(1);
-    groups[0].resize(ab.m);
-    for (uint32_t i = 0; i < ab.m; i++) groups[0][i] = i;
-    while (!groups.empty()) {
-        std::vector<uint8_t> pass = acc_check_groups(c, rs, sb, ab, groups);
-        std::vector<std::vector<uint32_t>> next;
-        for (size_t g = 0; g < groups.size(); g++) {
-            const std::vector<uint32_t> &grp = groups[g];
+    c.launches += 4;
+    LevelPlan plan;
+    plan.msm.resize(1);
+    plan.msm[0].members.resize(ab.m);
+    for (uint32_t i = 0; i < ab.m; i++) plan.msm[0].members[i] = i;
+    bool first = true;
+    for (int level = 0; plan.size(); level++) {
+        std::vector<uint8_t> pass = acc_check_groups(c, rs, sb, ab, plan, level);
+        if (first) {  // the stream has drained: the on-curve flag of the batch's points is on the host
+            first = false;
+            if (*h_bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
+        }
+        LevelPlan next;
+        for (size_t g = 0; g < plan.size(); g++) {
+            const std::vector<uint32_t> &grp = plan.at(g).members;
             if (pass[g]) {
                 for (uint32_t i : grp) ab.ok[i] = 1;
             } else if (grp.size() == 1) {
                 ab.ok[grp[0]] = 0;
             } else {
                 size_t part = grp.size() > 64 ? (grp.size() + 31) / 32 : std::max<size_t>(1, grp.size() / 8);
-                for (size_t at = 0; at < grp.size(); at += part)
-                    next.emplace_back(grp.begin() + at, grp.begin() + std::min(grp.size(), at + part));
+                const uint32_t sib_begin = (uint32_t)next.msm.size();
+                for (size_t at = 0; at < grp.size(); at += part) {
+                    LevelGroup child;
+                    child.members.assign(grp.begin() + at, grp.begin() + std::min(grp.size(), at + part));
+                    child.parent = (uint32_t)g;
+                    if (at + part >= grp.size()) {  // last child: A_parent minus its siblings
+                        child.derived = true;
+                        next.derived.push_back(std::move(child));
+                        next.derived_meta.push_back({(uint32_t)g, sib_begin, (uint32_t)next.msm.size()});
+                    } else {
+                        next.msm.push_back(std::move(child));
+                    }
+                }
             }
         }
-        groups.swap(next);
+        plan = std::move(next);
     }
 }
 
@@ -378,11 +528,9 @@ static void run_accumulators(Context &c, AccRun &rs, AccumulatorBatch &ab, int m
 // compute stream, a helper thread drives the step (Pallas) side on the second stream.  Holds the device lock.
 static void run_both_sides(Context &c, AccumulatorBatch &wrap, AccumulatorBatch &step, int mode, bool timing,
                            mina_b200_kernel_stats *stats_wrap, mina_b200_kernel_stats *stats_step) {
-    vstate();  // create the staging object before two threads race for it
     AccRun rw, rp;
-    rw.s = c.stream;
-    rp.s = c.copy_stream;
-    rw.timing = rp.timing = timing;
+    setup_run(c, rw, 0, timing);  // also creates the staging object before two threads race for it
+    setup_run(c, rp, 1, timing);
     std::exception_ptr err;
     std::thread helper([&]() {
         try {
@@ -898,8 +1046,7 @@ int mina_b200_accumulators_device(int curve, uint32_t m, const void *d_pre16, co
         std::lock_guard<std::mutex> lk(c.mu);
         CTX_CUDA_OK(cudaSetDevice(c.device));
         AccRun rs;
-        rs.s = c.stream;
-        rs.timing = stats != nullptr;
+        setup_run(c, rs, 0, stats != nullptr);
         try {
             run_accumulators(c, rs, ab, mode);
         } catch (...) {
