@@ -440,8 +440,6 @@ __global__ void __launch_bounds__(128) k_reduce_level(const xyzz *__restrict__ i
     outW[id] = acc;
 }
 
-// out[g] = sum of in[g*K .. g*K+K): one block per group, strided partial sums then a shared-memory
-// tree whose last five levels run on warp shuffles.
 template <class F>
 __device__ __forceinline__ xyzz shfl_down_point(const xyzz &p, int delta) {
     xyzz r;
@@ -454,64 +452,111 @@ __device__ __forceinline__ xyzz shfl_down_point(const xyzz &p, int delta) {
     }
     return r;
 }
-static constexpr int SUM_THREADS = 256;
+// sum over the warp of one point per lane (valid in lane 0); every lane must call it
 template <class F>
-__global__ void __launch_bounds__(SUM_THREADS) k_sum_points(const xyzz *__restrict__ in, xyzz *__restrict__ out, uint32_t K) {
-    __shared__ xyzz warp_part[SUM_THREADS / 32];
-    const xyzz *src = in + (size_t)blockIdx.x * K;
-    xyzz acc = Ec<F>::identity();
-    for (uint32_t i = threadIdx.x; i < K; i += SUM_THREADS) Ec<F>::add(acc, src[i]);
-#pragma unroll
+__device__ __forceinline__ xyzz warp_sum_points(xyzz acc) {
+#pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
         xyzz o = shfl_down_point<F>(acc, d);
         Ec<F>::add(acc, o);
     }
-    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) warp_part[wid] = acc;
-    __syncthreads();
-    if (wid == 0) {
-        acc = lane < SUM_THREADS / 32 ? warp_part[lane] : Ec<F>::identity();
-#pragma unroll
-        for (int d = 4; d >= 1; d >>= 1) {
-            xyzz o = shfl_down_point<F>(acc, d);
-            Ec<F>::add(acc, o);
-        }
-        if (lane == 0) out[blockIdx.x] = acc;
-    }
+    return acc;
 }
 
-struct FinalParams {
-    int levels;
-    int log_m[MAX_LEVELS];  // log2 of the chunk size used at each level
-    int W;                  // windows to Horner-combine per MSM (1 with the precomputed table)
+// ---- the tail of the bucket reduction: bit sums ------------------------------------------------------
+// After L running-sum passes a group is down to N = 2^nbits points B_t that still carry the weight t:
+//   Z = sum_t t * B_t = sum_k 2^k * U_k,   U_k = sum of the B_t whose index has bit k set.
+// The U_k are plain sums, all independent, so the latency-bound chain of further running-sum levels (5 x 2
+// launches, ~1.2 ms for one MSM in round 1) becomes ONE launch of independent warps plus a short Horner in
+// k_finalize.  The same launch also produces, as partial sums over <= 256 points each, T = sum_t B_t and
+// the sum of every pass's W values (which the old code took one launch per level for).
+// One warp per output: a lane walks its strided share, then a shuffle tree (a block-wide tree would spend
+// most of its additions on the tree itself: measured 4x slower at 77 groups).
+static constexpr uint32_t TAIL_ITEMS = 256;   // points per partial-sum warp
+static constexpr uint32_t TAIL_MAX_PARTS = 32;  // partials of one source (k_finalize adds them in one warp)
+static constexpr uint32_t TAIL_BITMAX = 512;  // bit sums start at <= 2^9 points per group
+struct TailParams {
+    int L;                       // running-sum passes done before the bit sums
+    int log_m[MAX_LEVELS];       // log2 of the chunk size of pass l
+    int nbits;                   // log2 of the points per group left after the passes
+    int W;                       // windows to Horner-combine per MSM (1 with the precomputed table)
     int c;
-    uint32_t groups;        // nmsm * W
+    uint32_t groups;             // nmsm * W
+    uint32_t slots;              // outputs per group
+    uint32_t parts_last;         // partials of T (slots nbits .. nbits + parts_last)
+    uint32_t w_n[MAX_LEVELS];    // W values per group written by pass l
+    uint32_t w_parts[MAX_LEVELS], w_slot[MAX_LEVELS];  // partials of sum W^l and their first slot
+    uint64_t w_off[MAX_LEVELS];  // where pass l's W values start inside the W buffer (in points)
 };
-// One thread per MSM: unwind the reduction levels, combine windows, normalise to affine.
-//   D_last = sumW[last];  D_l = sumW[l] + m_l * (D_{l+1} - T),  T = sum of all buckets of the group.
+static inline uint32_t tail_parts(uint32_t n) {
+    uint32_t p = (n + TAIL_ITEMS - 1) / TAIL_ITEMS;
+    return p < 1 ? 1 : (p > TAIL_MAX_PARTS ? TAIL_MAX_PARTS : p);
+}
+// out[g][slot]: slot < nbits -> U_slot; then the partials of T; then the partials of sum W^l per pass.
+template <class F>
+__global__ void __launch_bounds__(32) k_bit_sums(const xyzz *__restrict__ last, const xyzz *__restrict__ wbuf, TailParams tp,
+                                                 xyzz *__restrict__ out) {
+    const uint32_t g = blockIdx.x, slot = blockIdx.y, lane = threadIdx.x;
+    const uint32_t N = 1u << tp.nbits;
+    xyzz acc = Ec<F>::identity();
+    if (slot < (uint32_t)tp.nbits) {
+        const xyzz *src = last + (size_t)g * N;
+        const uint32_t mask = 1u << slot;
+        for (uint32_t i = lane; i < N / 2; i += 32) {
+            uint32_t t = ((i >> slot) << (slot + 1)) | mask | (i & (mask - 1u));
+            Ec<F>::add(acc, src[t]);
+        }
+    } else {
+        const xyzz *src = last + (size_t)g * N;
+        uint32_t n = N, parts = tp.parts_last, q = slot - tp.nbits;
+        for (int l = 0; l < tp.L; l++)
+            if (slot >= tp.w_slot[l]) {
+                n = tp.w_n[l];
+                parts = tp.w_parts[l];
+                q = slot - tp.w_slot[l];
+                src = wbuf + tp.w_off[l] + (size_t)g * n;
+            }
+        const uint32_t per = (n + parts - 1) / parts, begin = q * per, end = min(n, begin + per);
+        for (uint32_t t = begin + lane; t < end; t += 32) Ec<F>::add(acc, src[t]);
+    }
+    acc = warp_sum_points<F>(acc);
+    if (lane == 0) out[(size_t)g * tp.slots + slot] = acc;
+}
+
+// One warp per MSM: Horner over the bit sums (lane k doubles U_k k times, then a shuffle tree), unwind the
+// running-sum passes, combine windows, normalise.
+//   pass l turned points B with weights (b+1) into S (weights t) and W:  sum = sum W + m_l * sum_t t*S_t
+//   below the last pass the weights are t, above it they are (t+1):  D_l = sumW_l + m_l * (D_{l+1} - T).
 // AFFINE = false leaves the result in XYZZ form (no field inversion): callers that only COMPARE results
 // (the accumulator checks) cross-multiply instead of normalising.
 template <class F, bool AFFINE>
-__global__ void __launch_bounds__(64) k_finalize(const xyzz *__restrict__ sumW /* [levels][groups] */,
-                                                 const xyzz *__restrict__ total /* [groups] */, FinalParams fp,
-                                                 void *__restrict__ out_any, uint32_t nmsm) {
-    uint32_t msm = blockIdx.x * blockDim.x + threadIdx.x;
-    if (msm >= nmsm) return;
+__global__ void __launch_bounds__(32) k_finalize(const xyzz *__restrict__ sums /* [groups][slots] */, TailParams tp,
+                                                 void *__restrict__ out_any) {
+    const uint32_t msm = blockIdx.x, lane = threadIdx.x;
     xyzz res = Ec<F>::identity();
-    for (int w = fp.W - 1; w >= 0; w--) {
-        uint32_t g = msm * fp.W + w;
-        xyzz negT = total[g];
-        negT.y = Fd<F>::neg(negT.y);
-        xyzz D = sumW[(size_t)(fp.levels - 1) * fp.groups + g];
-        for (int l = fp.levels - 2; l >= 0; l--) {
-            Ec<F>::add(D, negT);
-            for (int k = 0; k < fp.log_m[l]; k++) D = Ec<F>::dbl(D);
-            Ec<F>::add(D, sumW[(size_t)l * fp.groups + g]);
+    for (int w = tp.W - 1; w >= 0; w--) {
+        const xyzz *base = sums + (size_t)(msm * tp.W + w) * tp.slots;
+        xyzz V = lane < (uint32_t)tp.nbits ? base[lane] : Ec<F>::identity();
+        for (uint32_t k = 0; k < lane && lane < (uint32_t)tp.nbits; k++) V = Ec<F>::dbl(V);
+        xyzz D = warp_sum_points<F>(V);  // Z = sum_t t * B_t
+        xyzz T = warp_sum_points<F>(lane < tp.parts_last ? base[tp.nbits + lane] : Ec<F>::identity());
+        if (tp.L == 0) {
+            Ec<F>::add(D, T);  // bucket b weighs b + 1
+        } else {
+            xyzz negT = T;
+            negT.y = Fd<F>::neg(negT.y);
+            for (int l = tp.L - 1; l >= 0; l--) {
+                if (l != tp.L - 1) Ec<F>::add(D, negT);
+                for (int k = 0; k < tp.log_m[l]; k++) D = Ec<F>::dbl(D);
+                xyzz Wl = warp_sum_points<F>(lane < tp.w_parts[l] ? base[tp.w_slot[l] + lane] : Ec<F>::identity());
+                Ec<F>::add(D, Wl);
+            }
         }
-        if (w != fp.W - 1)
-            for (int k = 0; k < fp.c; k++) res = Ec<F>::dbl(res);
+        if (w != tp.W - 1)
+            for (int k = 0; k < tp.c; k++) res = Ec<F>::dbl(res);
         Ec<F>::add(res, D);
     }
+    if (lane != 0) return;
     if (AFFINE)
         reinterpret_cast<affine *>(out_any)[msm] = Ec<F>::to_affine(res);
     else
@@ -626,17 +671,6 @@ class MsmEngine : public MsmEngineBase {
         if (cfg.leaf < 2 || (cfg.leaf & (cfg.leaf - 1))) throw std::runtime_error("msm: leaf must be a power of two");
         const int W = 255 / cfg.c + 1;
         const uint32_t nbw = 1u << (cfg.c - 1);
-        int levels = 0, log_m[MAX_LEVELS] = {0};
-        for (uint32_t N = nbw; N > 1;) {
-            int m = cfg.leaf;
-            while ((uint32_t)m > N) m >>= 1;
-            int lg = 0;
-            while ((1 << lg) < m) lg++;
-            if (levels >= MAX_LEVELS) throw std::runtime_error("msm: too many reduction levels");
-            log_m[levels++] = lg;
-            N /= m;
-        }
-        if (levels == 0) levels = 1;  // c == 1: a single bucket
         affine *table_new = nullptr;
         if (cfg.precompute) {
             if ((uint64_t)W * n >= (1ull << 31)) throw std::runtime_error("msm: table too large for 31-bit entries");
@@ -655,8 +689,7 @@ class MsmEngine : public MsmEngineBase {
             throw std::runtime_error("msm: too many bases");
         }
         // commit
-        bool same_plan = W == W_ && nbw == nbw_ && levels == levels_ && cfg.precompute == cfg_.precompute;
-        for (int l = 0; l < levels && same_plan; l++) same_plan = log_m[l] == log_m_[l];
+        const bool same_plan = W == W_ && nbw == nbw_ && cfg.leaf == cfg_.leaf && cfg.precompute == cfg_.precompute;
         free_dev(table_own_);
         table_own_ = table_new;
         table_ = cfg.precompute ? table_new : d_bases;
@@ -664,8 +697,6 @@ class MsmEngine : public MsmEngineBase {
         n_bases_ = n;
         W_ = W;
         nbw_ = nbw;
-        levels_ = levels;
-        for (int l = 0; l < MAX_LEVELS; l++) log_m_[l] = log_m[l];
         if (!same_plan) drop_workspace();  // the reduction plan sizes the level buffers
     }
 
@@ -728,7 +759,7 @@ class MsmEngine : public MsmEngineBase {
         free_dev(lvlS_[0]);
         free_dev(lvlS_[1]);
         free_dev(lvlW_);
-        free_dev(sumW_);
+        free_dev(sums_);
     }
     void release() {
         free_dev(table_own_);
@@ -737,6 +768,40 @@ class MsmEngine : public MsmEngineBase {
         for (cudaEvent_t e : ev_) cudaEventDestroy(e);
         ev_.clear();
     }
+
+    // chunk size of a running-sum pass over N points per group
+    int tail_log_m(uint32_t N) const {
+        int lg = 0;
+        while ((1 << (lg + 1)) <= cfg_.leaf && (2u << lg) <= N) lg++;
+        return lg;
+    }
+    TailParams plan_tail(uint32_t groups) const {
+        TailParams tp{};
+        uint32_t N = nbw_;
+        uint64_t off = 0;
+        while (N > TAIL_BITMAX) {
+            if (tp.L >= MAX_LEVELS) throw std::runtime_error("msm: too many reduction levels");
+            const int lg = tail_log_m(N);
+            tp.log_m[tp.L] = lg;
+            N >>= lg;
+            tp.w_n[tp.L] = N;
+            tp.w_off[tp.L] = off;
+            off += (uint64_t)groups * N;
+            tp.L++;
+        }
+        int nbits = 0;
+        while ((1u << nbits) < N) nbits++;
+        tp.nbits = nbits;
+        tp.parts_last = tail_parts(N);
+        tp.slots = (uint32_t)nbits + tp.parts_last;
+        for (int l = 0; l < tp.L; l++) {
+            tp.w_parts[l] = tail_parts(tp.w_n[l]);
+            tp.w_slot[l] = tp.slots;
+            tp.slots += tp.w_parts[l];
+        }
+        return tp;
+    }
+    uint32_t max_slots() const { return plan_tail(1).slots; }
 
     void run_src(int src, const uint32_t *d_src, int bpoly_k, uint32_t nmsm, uint32_t n_used, void *d_out, bool affine_out, cudaStream_t s) {
         if (!table_) throw std::runtime_error("msm: no bases set");
@@ -776,7 +841,9 @@ class MsmEngine : public MsmEngineBase {
         const uint32_t want_g = std::max<uint32_t>(groups, cap_groups_);
         drop_workspace();  // caps are zero from here until every allocation below has succeeded
         size_t ntiles = (want_b + SCAN_TILE - 1) / SCAN_TILE;
-        size_t first = (want_b >> log_m_[0]) + 1;
+        // level buffers: pass 0 writes want_b / m points, later passes a factor m fewer each (m >= 2)
+        const int lg0 = tail_log_m(nbw_);
+        size_t first = (want_b >> lg0) + 1;
         size_t bytes = 0;
         auto alloc = [&](auto &ptr, size_t b) {
             cudaError_t e = cudaMalloc(&ptr, b);
@@ -796,8 +863,8 @@ class MsmEngine : public MsmEngineBase {
         alloc(buckets_, want_b * sizeof(xyzz));
         alloc(lvlS_[0], first * sizeof(xyzz));
         alloc(lvlS_[1], first * sizeof(xyzz));
-        alloc(lvlW_, first * sizeof(xyzz));
-        alloc(sumW_, (size_t)MAX_LEVELS * want_g * sizeof(xyzz));
+        alloc(lvlW_, 2 * first * sizeof(xyzz));
+        alloc(sums_, (size_t)max_slots() * want_g * sizeof(xyzz));
         cap_buckets_ = want_b;
         cap_pairs_ = want_p;
         cap_groups_ = want_g;
@@ -862,45 +929,39 @@ class MsmEngine : public MsmEngineBase {
         k_accumulate_overflow<F><<<296, OVER_THREADS, 0, s>>>(over_list_, order_hist_ + ORDER_BINS, offsets_, pairs_, table_, buckets_);
         launches_++;
 
-        // running-sum levels
+        // running-sum passes while a group has more points than the bit sums should take, then the bit sums
+        TailParams tp = plan_tail(groups);
+        tp.W = cfg_.precompute ? 1 : W_;
+        tp.c = cfg_.c;
+        tp.groups = groups;
         const xyzz *in = buckets_;
         uint32_t N = nbw_;
-        xyzz *last_S = nullptr;
-        for (int l = 0; l < levels_; l++) {
-            int m = 1 << log_m_[l];
-            uint32_t outN = N / m;
-            uint32_t total_out = groups * outN;
+        for (int l = 0; l < tp.L; l++) {
+            const int m = 1 << tp.log_m[l];
+            const uint32_t total_out = groups * (N / m);
             xyzz *Sl = lvlS_[l & 1];
-            k_reduce_level<F><<<(total_out + 127) / 128, 128, 0, s>>>(in, Sl, lvlW_, total_out, m);
-            k_sum_points<F><<<groups, SUM_THREADS, 0, s>>>(lvlW_, sumW_ + (size_t)l * groups, outN);
-            launches_ += 2;
+            k_reduce_level<F><<<(total_out + 127) / 128, 128, 0, s>>>(in, Sl, lvlW_ + tp.w_off[l], total_out, m);
+            launches_++;
             in = Sl;
-            last_S = Sl;
-            N = outN;
+            N /= m;
         }
-        FinalParams fp;
-        fp.levels = levels_;
-        for (int l = 0; l < MAX_LEVELS; l++) fp.log_m[l] = l < levels_ ? log_m_[l] : 0;
-        fp.W = cfg_.precompute ? 1 : W_;
-        fp.c = cfg_.c;
-        fp.groups = groups;
+        k_bit_sums<F><<<dim3(groups, tp.slots), 32, 0, s>>>(in, lvlW_, tp, sums_);
         if (affine_out)
-            k_finalize<F, true><<<(nmsm + 63) / 64, 64, 0, s>>>(sumW_, last_S, fp, d_out, nmsm);
+            k_finalize<F, true><<<nmsm, 32, 0, s>>>(sums_, tp, d_out);
         else
-            k_finalize<F, false><<<(nmsm + 63) / 64, 64, 0, s>>>(sumW_, last_S, fp, d_out, nmsm);
-        launches_++;
+            k_finalize<F, false><<<nmsm, 32, 0, s>>>(sums_, tp, d_out);
+        launches_ += 2;
         CUDA_OK(cudaGetLastError());
     }
 
     MsmConfig cfg_;
     uint32_t n_bases_ = 0, nbw_ = 0;
-    int W_ = 0, levels_ = 0;
-    int log_m_[MAX_LEVELS] = {0};
+    int W_ = 0;
     const affine *table_ = nullptr;
     affine *table_own_ = nullptr;
     uint32_t *counters_ = nullptr, *offsets_ = nullptr, *tile_sums_ = nullptr, *pairs_ = nullptr, *err_ = nullptr;
     uint32_t *order_ = nullptr, *over_list_ = nullptr, *order_hist_ = nullptr;
-    xyzz *buckets_ = nullptr, *lvlS_[2] = {nullptr, nullptr}, *lvlW_ = nullptr, *sumW_ = nullptr;
+    xyzz *buckets_ = nullptr, *lvlS_[2] = {nullptr, nullptr}, *lvlW_ = nullptr, *sums_ = nullptr;
     uint64_t cap_buckets_ = 0, cap_pairs_ = 0;
     uint32_t cap_groups_ = 0;
     size_t ws_bytes_ = 0;

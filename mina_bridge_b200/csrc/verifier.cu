@@ -40,10 +40,10 @@ namespace pasta {
 // ---- persistent staging ---------------------------------------------------------------------------
 struct SideBuffers {  // one accumulator family (Vesta k=16 or Pallas k=15)
     PinnedBuf<uint8_t> h_pre, h_pts, h_r, h_out;
-    PinnedBuf<uint32_t> h_subset, h_bad;
+    PinnedBuf<uint32_t> h_subset, h_bad, h_soff;
     DevBuf<uint8_t> d_pre;
     DevBuf<fe> d_chal, d_r_can, d_r, d_tab, d_S, d_partial;
-    DevBuf<uint32_t> d_subset, d_pts_can, d_out_can, d_bad, d_sc;
+    DevBuf<uint32_t> d_subset, d_pts_can, d_out_can, d_bad, d_sc, d_soff;
     DevBuf<affine> d_pts, d_res;
     DevBuf<xyzz> d_xyzz, d_scaled;
 };
@@ -239,13 +239,13 @@ static void acc_per_proof(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBa
     for (uint32_t i = 0; i < ab.m; i++) ab.ok[i] = h_out[i];
 }
 
-// sum of the slices of each group: out[g][i] = sum_{s in [gso[g], gso[g+1])} partial[s][i]  (canonical)
+// sum of the kept slices of each group: out[g][i] = sum_{s in [gso[2g], gso[2g+1])} partial[s][i]  (canonical)
 template <class S>
 static __global__ void __launch_bounds__(256) k_sum_slices(const fe *__restrict__ partial, const uint32_t *__restrict__ gso, int k,
                                                            fe *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >> k) return;
-    uint32_t s0 = gso[blockIdx.y], s1 = gso[blockIdx.y + 1];
+    uint32_t s0 = gso[2 * blockIdx.y], s1 = gso[2 * blockIdx.y + 1];
     fe acc = fe_zero();
     for (uint32_t s = s0; s < s1; s++) acc = Fd<S>::add(acc, partial[((size_t)s << k) + i]);
     out[((size_t)blockIdx.y << k) + i] = acc;
@@ -304,14 +304,14 @@ static __device__ __forceinline__ xyzz block_sum_xyzz(xyzz acc, xyzz *warp_part)
     }
     return acc;
 }
-// D[g] = sum_{t in [goff[g], goff[g+1])} P[subset[t]]: one block per group
+// D[g] = sum_{j in [rng[2g], rng[2g+1])} P[j]: one block per group
 template <class F>
-static __global__ void __launch_bounds__(SUBSET_THREADS) k_subset_sums(const xyzz *__restrict__ P, const uint32_t *__restrict__ subset,
-                                                                       const uint32_t *__restrict__ goff, xyzz *__restrict__ out) {
+static __global__ void __launch_bounds__(SUBSET_THREADS) k_range_sums(const xyzz *__restrict__ P, const uint32_t *__restrict__ rng,
+                                                                      xyzz *__restrict__ out) {
     __shared__ xyzz warp_part[SUBSET_THREADS / 32];
-    const uint32_t t0 = goff[blockIdx.x], t1 = goff[blockIdx.x + 1];
+    const uint32_t t0 = rng[2 * blockIdx.x], t1 = rng[2 * blockIdx.x + 1];
     xyzz acc = Ec<F>::identity();
-    for (uint32_t t = t0 + threadIdx.x; t < t1; t += SUBSET_THREADS) Ec<F>::add(acc, P[subset[t]]);
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += SUBSET_THREADS) Ec<F>::add(acc, P[t]);
     acc = block_sum_xyzz<F>(acc, warp_part);
     if (threadIdx.x == 0) out[blockIdx.x] = acc;
 }
@@ -334,63 +334,78 @@ static __global__ void __launch_bounds__(SUBSET_THREADS) k_derive_last_child(con
     }
 }
 
-// One level of the group testing.  Groups that need an MSM come first, then the "derived" ones (last child
-// of each split parent, obtained by subtraction).
+// ---- group testing over index ranges ----------------------------------------------------------------
+// Every group is a contiguous range [a, b) of the batch.  Level 0 is the whole batch, combined in slices of
+// COMBINE_SLICE proofs whose partial vectors are KEPT: a later group that is a union of whole slices gets its
+// scalar vector by adding slices (k_sum_slices) instead of combining tables again.  A failing group is split
+// in two at a slice boundary while it is larger than two slices, in halves below that, and into singletons
+// at <= 4; the last child of every split needs no MSM (A_last = A_parent - siblings).
+static constexpr uint32_t COMBINE_SLICE = 64;
 struct LevelGroup {
-    std::vector<uint32_t> members;
-    uint32_t parent = 0;          // index into the previous level's group list
-    bool derived = false;
+    uint32_t a = 0, b = 0;
+    uint32_t parent = 0;  // index into the previous level's group list
+    uint32_t size() const { return b - a; }
 };
 struct LevelPlan {
-    std::vector<LevelGroup> msm, derived;
-    std::vector<std::array<uint32_t, 3>> derived_meta;  // parent, sibling range among `msm`
-    size_t size() const { return msm.size() + derived.size(); }
-    const LevelGroup &at(size_t g) const { return g < msm.size() ? msm[g] : derived[g - msm.size()]; }
+    // groups in result order: MSM groups built from kept slices, MSM groups combined from tables, derived groups
+    std::vector<LevelGroup> sliced, combined, derived;
+    std::vector<std::array<uint32_t, 3>> derived_meta;  // parent, sibling range in MSM order
+    size_t n_msm() const { return sliced.size() + combined.size(); }
+    size_t size() const { return n_msm() + derived.size(); }
+    const LevelGroup &at(size_t g) const {
+        if (g < sliced.size()) return sliced[g];
+        g -= sliced.size();
+        return g < combined.size() ? combined[g] : derived[g - combined.size()];
+    }
 };
+static bool slice_aligned(const LevelGroup &g, uint32_t m) { return g.a % COMBINE_SLICE == 0 && (g.b % COMBINE_SLICE == 0 || g.b == m); }
 
 // One level of random-linear-combination checks, ALL groups in one launch set:
 //   pass[g]  <=>  < sum_{j in g} r_j b_poly_coefficients(chals_j), G >  ==  sum_{j in g} r_j C_j.
-// g side: k_bpoly_combine over slices of <= 64 proofs (so a single large group still fills the GPU),
-// k_sum_slices, then ONE batched MSM (nmsm = #groups that need one) over the resident SRS; derived groups
-// by subtraction.  Commitment side: sums of the precomputed P_j = r_j C_j.
-static constexpr uint32_t COMBINE_SLICE = 64;
+// g side: scalar vectors from kept slices or k_bpoly_combine, then ONE batched MSM (nmsm = #groups that need
+// one) over the resident SRS; derived groups by subtraction.  Commitment side: sums of the precomputed
+// P_j = r_j C_j.
 static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab, const LevelPlan &plan,
-                                             int parity) {
+                                             int level) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
-    const uint32_t Gm = (uint32_t)plan.msm.size(), Gd = (uint32_t)plan.derived.size(), G = Gm + Gd;
-    // one upload: subset (all groups) | slice_off (MSM groups) | gso (MSM groups) | goff (all groups) | derived triples
-    std::vector<uint32_t> meta, slice_off{0}, gso{0}, goff{0};
-    for (uint32_t g = 0; g < G; g++) {
-        const std::vector<uint32_t> &mem = plan.at(g).members;
-        if (g < Gm) {
-            for (size_t at = 0; at < mem.size(); at += COMBINE_SLICE)
-                slice_off.push_back((uint32_t)(meta.size() + std::min(mem.size(), at + COMBINE_SLICE)));
-            gso.push_back((uint32_t)slice_off.size() - 1);
-        }
-        meta.insert(meta.end(), mem.begin(), mem.end());
-        goff.push_back((uint32_t)meta.size());
+    const uint32_t Gs = (uint32_t)plan.sliced.size(), Gc = (uint32_t)plan.combined.size(), Gm = Gs + Gc;
+    const uint32_t Gd = (uint32_t)plan.derived.size(), G = Gm + Gd;
+    const uint32_t n_slices0 = (ab.m + COMBINE_SLICE - 1) / COMBINE_SLICE;
+    // one upload: slice ranges of the sliced groups (Gs + 1 entries are not enough: ranges need not be adjacent, so
+    // 2 per group) | combine subset | combine group offsets | P ranges of all groups (2 per group) | derived triples
+    std::vector<uint32_t> meta;
+    const size_t o_sl = meta.size();
+    for (auto &g : plan.sliced) {
+        meta.push_back(g.a / COMBINE_SLICE);
+        meta.push_back((g.b + COMBINE_SLICE - 1) / COMBINE_SLICE);
     }
-    const uint32_t nsub_all = (uint32_t)meta.size(), nsub_msm = slice_off.back(), S = (uint32_t)slice_off.size() - 1;
-    const size_t o_slice = meta.size();
-    meta.insert(meta.end(), slice_off.begin(), slice_off.end());
-    const size_t o_gso = meta.size();
-    meta.insert(meta.end(), gso.begin(), gso.end());
-    const size_t o_goff = meta.size();
-    meta.insert(meta.end(), goff.begin(), goff.end());
+    const size_t o_sub = meta.size();
+    std::vector<uint32_t> coff{0};
+    uint32_t nsub = 0;
+    for (auto &g : plan.combined) {
+        for (uint32_t j = g.a; j < g.b; j++) meta.push_back(j);
+        nsub += g.size();
+        coff.push_back(nsub);
+    }
+    const size_t o_coff = meta.size();
+    meta.insert(meta.end(), coff.begin(), coff.end());
+    const size_t o_rng = meta.size();
+    for (uint32_t g = 0; g < G; g++) {
+        meta.push_back(plan.at(g).a);
+        meta.push_back(plan.at(g).b);
+    }
     const size_t o_der = meta.size();
     for (auto &d : plan.derived_meta) meta.insert(meta.end(), d.begin(), d.end());
-    (void)nsub_all;
     uint32_t *h_meta = sb.h_subset.reserve(meta.size());
     std::memcpy(h_meta, meta.data(), meta.size() * 4);
     uint32_t *d_meta = sb.d_subset.reserve(meta.size());
     // XYZZ scratch: [A even | A odd | D], each ab.m long (groups are disjoint and non-empty: G <= m)
     xyzz *d_x = sb.d_xyzz.reserve(3 * (size_t)ab.m);
-    xyzz *d_A = d_x + (size_t)(parity & 1) * ab.m, *d_A_prev = d_x + (size_t)((parity & 1) ^ 1) * ab.m, *d_D = d_x + 2 * (size_t)ab.m;
+    xyzz *d_A = d_x + (size_t)(level & 1) * ab.m, *d_A_prev = d_x + (size_t)((level & 1) ^ 1) * ab.m, *d_D = d_x + 2 * (size_t)ab.m;
     uint8_t *d_ok = reinterpret_cast<uint8_t *>(sb.d_out_can.reserve((G + 3) / 4 + 1));
-    fe *d_S = sb.d_S.reserve((size_t)Gm << ab.k);
-    const bool sliced = S != Gm;
-    fe *d_partial = sliced ? sb.d_partial.reserve((size_t)S << ab.k) : d_S;
+    fe *d_S = sb.d_S.reserve((size_t)std::max<uint32_t>(Gm, 1) << ab.k);
+    fe *d_partial = sb.d_partial.reserve((size_t)n_slices0 << ab.k);  // level-0 slices, kept for the whole batch
     uint8_t *h_out = sb.h_out.reserve(G);
     CTX_CUDA_OK(cudaMemcpyAsync(d_meta, h_meta, meta.size() * 4, cudaMemcpyHostToDevice, rs.s));
     if (rs.timing) {
@@ -400,15 +415,32 @@ static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers
         }
         CTX_CUDA_OK(cudaEventRecord(rs.ev[0], rs.s));
     }
-    launch_bpoly_combine(field, sb.d_tab.p, d_meta, d_meta + o_slice, S, nsub_msm, ab.k, d_partial, rs.s);
+    uint32_t combine_proofs = 0, combine_vectors = 0;
+    if (level == 0) {  // slices of the whole batch, in place (subset == nullptr: proof j is table j)
+        std::vector<uint32_t> soff(n_slices0 + 1);
+        for (uint32_t i = 0; i <= n_slices0; i++) soff[i] = std::min(ab.m, i * COMBINE_SLICE);
+        uint32_t *h_soff = sb.h_soff.reserve(soff.size());
+        std::memcpy(h_soff, soff.data(), soff.size() * 4);
+        uint32_t *d_soff = sb.d_soff.reserve(soff.size());
+        CTX_CUDA_OK(cudaMemcpyAsync(d_soff, h_soff, soff.size() * 4, cudaMemcpyHostToDevice, rs.s));
+        launch_bpoly_combine(field, sb.d_tab.p, nullptr, d_soff, n_slices0, ab.m, ab.k, d_partial, rs.s);
+        c.launches += 1;
+        combine_proofs += ab.m;
+        combine_vectors += n_slices0;
+    }
+    if (Gc) {
+        launch_bpoly_combine(field, sb.d_tab.p, d_meta + o_sub, d_meta + o_coff, Gc, nsub, ab.k, d_S + ((size_t)Gs << ab.k), rs.s);
+        c.launches += 1;
+        combine_proofs += nsub;
+        combine_vectors += Gc;
+    }
     if (rs.timing) CTX_CUDA_OK(cudaEventRecord(rs.ev[1], rs.s));
-    c.launches += 1;
-    if (sliced) {
-        dim3 grid(((1u << ab.k) + 255) / 256, Gm);
+    if (Gs) {
+        dim3 grid(((1u << ab.k) + 255) / 256, Gs);
         if (field == 0)
-            k_sum_slices<FpParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + o_gso, ab.k, d_S);
+            k_sum_slices<FpParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + o_sl, ab.k, d_S);
         else
-            k_sum_slices<FqParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + o_gso, ab.k, d_S);
+            k_sum_slices<FqParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + o_sl, ab.k, d_S);
         c.launches += 1;
     }
     cc.fixed->enable_kernel_timing(rs.timing);
@@ -418,11 +450,11 @@ static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers
         rs.scaled_ready = nullptr;
     }
     if (ab.curve == 0) {
-        k_subset_sums<FpParams><<<G, SUBSET_THREADS, 0, rs.s>>>(sb.d_scaled.p, d_meta, d_meta + o_goff, d_D);
+        k_range_sums<FpParams><<<G, SUBSET_THREADS, 0, rs.s>>>(sb.d_scaled.p, d_meta + o_rng, d_D);
         if (Gd) k_derive_last_child<FpParams><<<Gd, SUBSET_THREADS, 0, rs.s>>>(d_A_prev, d_A, d_meta + o_der, Gm);
         k_xyzz_pairs_equal<FpParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_A, d_D, G, d_ok);
     } else {
-        k_subset_sums<FqParams><<<G, SUBSET_THREADS, 0, rs.s>>>(sb.d_scaled.p, d_meta, d_meta + o_goff, d_D);
+        k_range_sums<FqParams><<<G, SUBSET_THREADS, 0, rs.s>>>(sb.d_scaled.p, d_meta + o_rng, d_D);
         if (Gd) k_derive_last_child<FqParams><<<Gd, SUBSET_THREADS, 0, rs.s>>>(d_A_prev, d_A, d_meta + o_der, Gm);
         k_xyzz_pairs_equal<FqParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_A, d_D, G, d_ok);
     }
@@ -437,17 +469,35 @@ static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers
         rs.stats.accumulate_ms += cc.fixed->last_accumulate_ms();
         rs.stats.msm_points += (uint64_t)Gm << ab.k;
         rs.stats.msm_count += Gm;
-        rs.stats.combine_proofs += nsub_msm;
-        rs.stats.combine_vectors += S;
+        rs.stats.combine_proofs += combine_proofs;
+        rs.stats.combine_vectors += combine_vectors;
     }
     std::vector<uint8_t> pass(G);
     for (uint32_t g = 0; g < G; g++) pass[g] = h_out[g];
     return pass;
 }
 
-// Group testing in levels: the whole batch first (the common case ends here: one combine + one MSM), then
-// failing groups are split ~32-ways while they are large and 8-ways below 64, every level being ONE batched
-// launch set.  A failing singleton is a bad proof: r != 0, so r*A == r*C <=> A == C.
+// where a failing group [a, b) is cut: children in order; the last one is the derived child
+static std::vector<uint32_t> split_points(uint32_t a, uint32_t b) {
+    const uint32_t size = b - a;
+    std::vector<uint32_t> cuts;
+    if (size <= 4) {
+        for (uint32_t j = a + 1; j < b; j++) cuts.push_back(j);
+    } else if (size > 2 * COMBINE_SLICE) {
+        // halve at a slice boundary so that both children can be built from kept slices
+        uint32_t mid = a + size / 2;
+        mid = (mid + COMBINE_SLICE - 1) / COMBINE_SLICE * COMBINE_SLICE;
+        if (mid <= a || mid >= b) mid = a + size / 2;
+        cuts.push_back(mid);
+    } else {
+        cuts.push_back(a + (size + 1) / 2);
+    }
+    return cuts;
+}
+
+// Group testing in levels: the whole batch first (the common case ends here: one combine + one MSM), then failing
+// groups are halved, every level being ONE batched launch set (~k log2(n/k) MSMs for k bad proofs of n).
+// A failing singleton is a bad proof: r != 0, so r*A == r*C <=> A == C.
 static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;
     AccDevice dv = acc_prepare(c, rs, sb, ab);
@@ -476,39 +526,49 @@ static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &a
     launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, d_r, false, rs.s);
     c.launches += 4;
     LevelPlan plan;
-    plan.msm.resize(1);
-    plan.msm[0].members.resize(ab.m);
-    for (uint32_t i = 0; i < ab.m; i++) plan.msm[0].members[i] = i;
-    bool first = true;
+    plan.sliced.resize(1);
+    plan.sliced[0].a = 0;
+    plan.sliced[0].b = ab.m;
     for (int level = 0; plan.size(); level++) {
         std::vector<uint8_t> pass = acc_check_groups(c, rs, sb, ab, plan, level);
-        if (first) {  // the stream has drained: the on-curve flag of the batch's points is on the host
-            first = false;
-            if (*h_bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
-        }
+        // the stream has drained: the on-curve flag of the batch's points is on the host
+        if (level == 0 && *h_bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
         LevelPlan next;
+        struct Pending {
+            uint32_t parent, list, begin, end;  // siblings [begin, end) inside list 0 (sliced) or 1 (combined)
+        };
+        std::vector<Pending> pend;
         for (size_t g = 0; g < plan.size(); g++) {
-            const std::vector<uint32_t> &grp = plan.at(g).members;
+            const LevelGroup &grp = plan.at(g);
             if (pass[g]) {
-                for (uint32_t i : grp) ab.ok[i] = 1;
+                for (uint32_t i = grp.a; i < grp.b; i++) ab.ok[i] = 1;
             } else if (grp.size() == 1) {
-                ab.ok[grp[0]] = 0;
+                ab.ok[grp.a] = 0;
             } else {
-                size_t part = grp.size() > 64 ? (grp.size() + 31) / 32 : std::max<size_t>(1, grp.size() / 8);
-                const uint32_t sib_begin = (uint32_t)next.msm.size();
-                for (size_t at = 0; at < grp.size(); at += part) {
-                    LevelGroup child;
-                    child.members.assign(grp.begin() + at, grp.begin() + std::min(grp.size(), at + part));
-                    child.parent = (uint32_t)g;
-                    if (at + part >= grp.size()) {  // last child: A_parent minus its siblings
-                        child.derived = true;
-                        next.derived.push_back(std::move(child));
-                        next.derived_meta.push_back({(uint32_t)g, sib_begin, (uint32_t)next.msm.size()});
-                    } else {
-                        next.msm.push_back(std::move(child));
-                    }
+                std::vector<uint32_t> cuts = split_points(grp.a, grp.b);
+                // the MSM children of one parent all go to the same list so that they stay adjacent
+                bool all_sliced = true;
+                uint32_t lo = grp.a;
+                for (uint32_t cut : cuts) {
+                    LevelGroup child{lo, cut, (uint32_t)g};
+                    all_sliced = all_sliced && slice_aligned(child, ab.m);
+                    lo = cut;
                 }
+                std::vector<LevelGroup> &list = all_sliced ? next.sliced : next.combined;
+                Pending pd{(uint32_t)g, all_sliced ? 0u : 1u, (uint32_t)list.size(), 0};
+                lo = grp.a;
+                for (uint32_t cut : cuts) {
+                    list.push_back(LevelGroup{lo, cut, (uint32_t)g});
+                    lo = cut;
+                }
+                pd.end = (uint32_t)list.size();
+                pend.push_back(pd);
+                next.derived.push_back(LevelGroup{lo, grp.b, (uint32_t)g});
             }
+        }
+        for (const Pending &pd : pend) {
+            const uint32_t shift = pd.list ? (uint32_t)next.sliced.size() : 0u;
+            next.derived_meta.push_back({pd.parent, pd.begin + shift, pd.end + shift});
         }
         plan = std::move(next);
     }
