@@ -34,7 +34,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH = 1024              # proofs per step, whole job (BASELINE.json configs[3] / north_star target)
-CORRUPT_EVERY = 101       # proofs i with i % 101 == 7 get one flipped prechallenge bit (10 of 1024)
+N_CORRUPT = 10            # 1 % of the batch gets one flipped prechallenge bit, at seeded random positions
+CORRUPT_SEED = 0x4D494E41
 ALG_BYTES_PER_POINT = 96  # 64 B affine base + 32 B scalar
 OFF_WRAP_PRE, OFF_WRAP_X, OFF_WRAP_Y = 73, 374, 414
 OFF_STEP_PRE, OFF_STEP_SG = 446, 934
@@ -79,12 +80,19 @@ def golden(name):
     return open(os.path.join(ROOT, "tests", "golden", name), "rb").read()
 
 
-def synth_batch():
+def corrupt_positions(n_corrupt=N_CORRUPT):
+    import random
+
+    return set(random.Random(CORRUPT_SEED).sample(range(BATCH), n_corrupt))
+
+
+def synth_batch(n_corrupt=N_CORRUPT):
     """The fixed 1024-proof batch: (proofs, pubs, expected built-stage bit)."""
     proof, pub = golden("mina_state.proof"), golden("mina_state.pub")
+    bad = corrupt_positions(n_corrupt)
     proofs, want = [], []
     for i in range(BATCH):
-        if i % CORRUPT_EVERY == 7:
+        if i in bad:
             m = bytearray(proof)
             m[OFF_WRAP_PRE + (i % 256)] ^= 1 << (i % 8)
             proofs.append(bytes(m))
@@ -254,6 +262,21 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
     pp_steps = max(2, min(a.steps, 4))
     t_pp, kms_pp = timed(lambda: step_device(mb.MODE_PER_PROOF, True), pp_steps)
     t_pp_e2e, _ = timed(lambda: step_e2e(mb.MODE_PER_PROOF), pp_steps)
+    # the same batch with no / one corrupted member (device-resident leg only): how the group testing scales down
+    other = {}
+    for label, nc in (("all_valid", 0), ("one_corrupted", 1)):
+        o_proofs, _, o_want = synth_batch(nc)
+        o_dev = device_inputs([o_proofs[i] for i in mine], torch, dev)
+        o_expect = torch.tensor(o_want, dtype=torch.uint8, device=dev)
+
+        def o_step():
+            ok3 = mb.state_accumulators_device(m, *[t.data_ptr() for t in o_dev], mb.MODE_RLC, False)
+            reduce_bits(bytes(ok3[3 * i] & ok3[3 * i + 1] & ok3[3 * i + 2] for i in range(m)))
+
+        o_step()
+        assert torch.equal(result, o_expect), "%s batch: result bytes differ from the expected bits" % label
+        t_o, _ = timed(o_step, a.steps)
+        other[label] = {"value": BATCH * a.steps / t_o, "unit": UNIT, "ms_per_step": t_o / a.steps * 1e3, "corrupted": nc}
     sampler.stop.set()
     sampler.join()
     if a.profile_step:
@@ -301,12 +324,13 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
         "metric": METRIC, "value": BATCH * a.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
         "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u256 modular (8x32 Montgomery)", "data": "synthetic",
-        "config": {"workload": "state1024: 1024 serialized proof-of-state inputs per step (reference fixture x1024, 10 with a flipped prechallenge bit), rank r takes i = r mod N, one NCCL all-reduce(MIN) of 1024 result bytes per step",
+        "config": {"workload": "state1024: 1024 serialized proof-of-state inputs per step (reference fixture x1024, 10 at seeded random positions with a flipped prechallenge bit; `other_batches` = none / one corrupted), rank r takes i = r mod N, one NCCL all-reduce(MIN) of 1024 result bytes per step",
                    "mode": "rlc (random linear combination over the shard + bisection; per-proof numbers in `per_proof_mode`)",
                    "built_stages": BUILT, "absent_stages": ABSENT,
                    "l2": "per-step working set: %d x 16 KiB product tables + 64 MiB / 32 MiB fixed-base tables > 126 MB L2 together; inputs differ per proof only in 10 members" % (3 * m)},
         "roofline": dominant,
         "other_kernels": [comb_rlc if dominant is acc_rlc else acc_rlc],
+        "other_batches": other,
         "per_proof_mode": {"value": BATCH * pp_steps / t_pp, "e2e": BATCH * pp_steps / t_pp_e2e, "unit": UNIT, "steps": pp_steps,
                            "ms_per_step": t_pp / pp_steps * 1e3, "roofline": acc_pp},
         "cpu_baseline": {"value": cpu, "unit": UNIT, "cores": cores, "kind": "port", "single_thread_value": cpu1, "modmul_ns": modmul_ns,

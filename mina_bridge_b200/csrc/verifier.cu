@@ -40,7 +40,7 @@ namespace pasta {
 // ---- persistent staging ---------------------------------------------------------------------------
 struct SideBuffers {  // one accumulator family (Vesta k=16 or Pallas k=15)
     PinnedBuf<uint8_t> h_pre, h_pts, h_r, h_out;
-    PinnedBuf<uint32_t> h_subset, h_bad, h_soff;
+    PinnedBuf<uint32_t> h_subset, h_bad, h_soff, h_status;
     DevBuf<uint8_t> d_pre;
     DevBuf<fe> d_chal, d_r_can, d_r, d_tab, d_S, d_partial;
     DevBuf<uint32_t> d_subset, d_pts_can, d_out_can, d_bad, d_sc, d_soff;
@@ -168,7 +168,6 @@ static __global__ void __launch_bounds__(128) k_xyzz_pairs_equal(const xyzz *__r
 struct AccRun {
     cudaStream_t s = nullptr, aux = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;  // owned by VerifierState (created once)
-    cudaEvent_t scaled_ready = nullptr;          // set while the P_j of this batch are still in flight on `aux`
     bool timing = false;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     mina_b200_kernel_stats stats{0.f, 0.f, 0, 0, 0, 0};
@@ -254,7 +253,7 @@ static __global__ void __launch_bounds__(256) k_sum_slices(const fe *__restrict_
 // ---- commitment side of the random linear combination ----------------------------------------------
 // P_j = r_j * C_j once per batch (r_j < 2^128: plain double-and-add, one thread per point, left in XYZZ).
 // It runs on the pipeline's auxiliary stream beside the table / combine / MSM work of level 0; every
-// level then only needs sums of P_j over its groups (k_subset_sums), not another MSM.
+// level then only needs sums of P_j over its groups (k_range_sums), not another MSM.
 template <class F>
 static __global__ void __launch_bounds__(64) k_scale_points_128(const affine *__restrict__ pts, const fe *__restrict__ r_can, uint32_t m,
                                                                 xyzz *__restrict__ out) {
@@ -269,6 +268,31 @@ static __global__ void __launch_bounds__(64) k_scale_points_128(const affine *__
         if ((r.v[b >> 5] >> (b & 31)) & 1u) Ec<F>::add_mixed(acc, q);
     }
     out[i] = acc;
+}
+// w * p for a small scalar (w < 2^31), XYZZ in and out
+template <class F>
+static __device__ __forceinline__ xyzz small_mul(const xyzz &p, uint32_t w) {
+    xyzz acc = Ec<F>::identity();
+#pragma unroll 1
+    for (int b = 31 - __clz(w | 1u); b >= 0; b--) {
+        acc = Ec<F>::dbl(acc);
+        if ((w >> b) & 1u) Ec<F>::add(acc, p);
+    }
+    return acc;
+}
+// The locator weights: proof j of the batch weighs j + 1.  Pw_j = (j + 1) * P_j,  rw_j = (j + 1) * r_j.
+template <class F>
+static __global__ void __launch_bounds__(64) k_weight_points(const xyzz *__restrict__ P, uint32_t m, xyzz *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = small_mul<F>(P[i], i + 1u);
+}
+template <class S>
+static __global__ void __launch_bounds__(128) k_weight_scalars(const fe *__restrict__ r_mont, uint32_t m, fe *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    fe w = fe_zero();
+    w.v[0] = i + 1u;
+    out[i] = Fd<S>::mul(r_mont[i], Fd<S>::to_mont(w));
 }
 template <class F>
 static __device__ __forceinline__ xyzz shfl_down_xyzz(const xyzz &p, int delta) {
@@ -304,24 +328,29 @@ static __device__ __forceinline__ xyzz block_sum_xyzz(xyzz acc, xyzz *warp_part)
     }
     return acc;
 }
-// D[g] = sum_{j in [rng[2g], rng[2g+1])} P[j]: one block per group
+// D[which][g] = sum_{j in [rng[2g], rng[2g+1])} P_which[j]: one block per (group, which); which = blockIdx.y
+// selects the plain points (0) or the weighted ones (1); the outputs are `stride` apart.
 template <class F>
-static __global__ void __launch_bounds__(SUBSET_THREADS) k_range_sums(const xyzz *__restrict__ P, const uint32_t *__restrict__ rng,
-                                                                      xyzz *__restrict__ out) {
+static __global__ void __launch_bounds__(SUBSET_THREADS) k_range_sums(const xyzz *__restrict__ P0, const xyzz *__restrict__ P1,
+                                                                      const uint32_t *__restrict__ rng, xyzz *__restrict__ out, uint32_t stride) {
     __shared__ xyzz warp_part[SUBSET_THREADS / 32];
+    const xyzz *P = blockIdx.y ? P1 : P0;
     const uint32_t t0 = rng[2 * blockIdx.x], t1 = rng[2 * blockIdx.x + 1];
     xyzz acc = Ec<F>::identity();
     for (uint32_t t = t0 + threadIdx.x; t < t1; t += SUBSET_THREADS) Ec<F>::add(acc, P[t]);
     acc = block_sum_xyzz<F>(acc, warp_part);
-    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+    if (threadIdx.x == 0) out[(size_t)blockIdx.y * stride + blockIdx.x] = acc;
 }
 // The last child of every split group needs no MSM:  A_last = A_parent - sum of its siblings' A.
 // derived[3*d + {0,1,2}] = parent index in `A_prev`, [sib_begin, sib_end) in `A` (this level's MSM results);
-// the result goes to A[n_msm + d].  One block per derived group.
+// the result goes to A[n_msm + d].  One block per (derived group, which); the plain and the weighted arrays
+// are `stride` apart.
 template <class F>
 static __global__ void __launch_bounds__(SUBSET_THREADS) k_derive_last_child(const xyzz *__restrict__ A_prev, xyzz *__restrict__ A,
-                                                                             const uint32_t *__restrict__ derived, uint32_t n_msm) {
+                                                                             const uint32_t *__restrict__ derived, uint32_t n_msm, uint32_t stride) {
     __shared__ xyzz warp_part[SUBSET_THREADS / 32];
+    A_prev += (size_t)blockIdx.y * stride;
+    A += (size_t)blockIdx.y * stride;
     const uint32_t parent = derived[3 * blockIdx.x], s0 = derived[3 * blockIdx.x + 1], s1 = derived[3 * blockIdx.x + 2];
     xyzz acc = Ec<F>::identity();
     for (uint32_t t = s0 + threadIdx.x; t < s1; t += SUBSET_THREADS) Ec<F>::add(acc, A[t]);
@@ -333,14 +362,70 @@ static __global__ void __launch_bounds__(SUBSET_THREADS) k_derive_last_child(con
         A[n_msm + blockIdx.x] = p;
     }
 }
+template <class F>
+static __device__ __forceinline__ bool xyzz_equal(const xyzz &p, const xyzz &q) {
+    bool pi = fe_is_zero(p.zz), qi = fe_is_zero(q.zz);
+    if (pi || qi) return pi && qi;
+    return fe_eq(Fd<F>::mul(p.x, q.zz), Fd<F>::mul(q.x, p.zz)) && fe_eq(Fd<F>::mul(p.y, q.zzz), Fd<F>::mul(q.y, p.zzz));
+}
+// Verdict of one group from its two error sums
+//   T0 = A0 - D0 = sum_{j in g} r_j e_j,   T1 = A1 - D1 = sum_{j in g} (j + 1) r_j e_j,   e_j = <s_j, G> - C_j:
+//   T0 == 0                        -> every proof of the group is good                          (status 1)
+//   T1 == w * T0, w - 1 in [a, b)  -> proof w - 1 is the ONLY bad one of the group               (status 2 + w - 1)
+//   otherwise                      -> at least two bad proofs (or no locator at this level)      (status 0)
+// Why the middle case is sound: with two or more e_j != 0 the relation sum_j (j + 1 - w) r_j e_j = 0 is, for each
+// fixed w, a non-trivial linear equation in independent 128-bit r_j chosen after the proofs: probability
+// <= 2^-128 per w, <= 2^-118 over the <= 1024 candidates.  (Single-error location in a batch, Law & Matt 2007.)
+static constexpr int LOCATE_THREADS = 128;
+template <class F>
+static __global__ void __launch_bounds__(LOCATE_THREADS) k_locate(const xyzz *__restrict__ A, const xyzz *__restrict__ D, uint32_t stride,
+                                                                  const uint32_t *__restrict__ rng, int with_locator,
+                                                                  uint32_t *__restrict__ status) {
+    __shared__ uint32_t found;
+    const uint32_t g = blockIdx.x, a = rng[2 * g], b = rng[2 * g + 1];
+    if (threadIdx.x == 0) found = 0;
+    __syncthreads();
+    xyzz T0 = A[g], nD = D[g];
+    nD.y = Fd<F>::neg(nD.y);
+    Ec<F>::add(T0, nD);
+    if (Ec<F>::is_identity(T0)) {
+        if (threadIdx.x == 0) status[g] = 1;
+        return;
+    }
+    if (!with_locator) {
+        if (threadIdx.x == 0) status[g] = 0;
+        return;
+    }
+    xyzz T1 = A[stride + g];
+    nD = D[stride + g];
+    nD.y = Fd<F>::neg(nD.y);
+    Ec<F>::add(T1, nD);
+    // thread t tries w = a + 1 + t, then strides by the block size (one addition per further candidate)
+    uint32_t w = a + 1u + threadIdx.x;
+    if (w <= b) {
+        xyzz X = small_mul<F>(T0, w);
+        const xyzz step = (w + LOCATE_THREADS <= b) ? small_mul<F>(T0, LOCATE_THREADS) : Ec<F>::identity();
+        for (;;) {
+            if (xyzz_equal<F>(X, T1)) atomicMax(&found, w);
+            w += LOCATE_THREADS;
+            if (w > b) break;
+            Ec<F>::add(X, step);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) status[g] = found ? 2u + (found - 1u) : 0u;
+}
 
 // ---- group testing over index ranges ----------------------------------------------------------------
 // Every group is a contiguous range [a, b) of the batch.  Level 0 is the whole batch, combined in slices of
 // COMBINE_SLICE proofs whose partial vectors are KEPT: a later group that is a union of whole slices gets its
-// scalar vector by adding slices (k_sum_slices) instead of combining tables again.  A failing group is split
-// in two at a slice boundary while it is larger than two slices, in halves below that, and into singletons
-// at <= 4; the last child of every split needs no MSM (A_last = A_parent - siblings).
+// scalar vector by adding slices (k_sum_slices) instead of combining tables again.  If level 0 fails, every
+// later level computes TWO sums per group (plain and locator-weighted, see k_locate), so a group with a single
+// bad proof is resolved by one test instead of log2(size) halvings; a group with more is split (wide while few
+// groups are open, so the launch set fills the GPU; at slice boundaries while groups are large).  The last
+// child of every split needs no MSM (A_last = A_parent - siblings).
 static constexpr uint32_t COMBINE_SLICE = 64;
+static constexpr uint32_t SPLIT_TARGET = 16;  // open groups x children per level the splits aim for
 struct LevelGroup {
     uint32_t a = 0, b = 0;
     uint32_t parent = 0;  // index into the previous level's group list
@@ -360,20 +445,25 @@ struct LevelPlan {
 };
 static bool slice_aligned(const LevelGroup &g, uint32_t m) { return g.a % COMBINE_SLICE == 0 && (g.b % COMBINE_SLICE == 0 || g.b == m); }
 
-// One level of random-linear-combination checks, ALL groups in one launch set:
-//   pass[g]  <=>  < sum_{j in g} r_j b_poly_coefficients(chals_j), G >  ==  sum_{j in g} r_j C_j.
-// g side: scalar vectors from kept slices or k_bpoly_combine, then ONE batched MSM (nmsm = #groups that need
-// one) over the resident SRS; derived groups by subtraction.  Commitment side: sums of the precomputed
-// P_j = r_j C_j.
-static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab, const LevelPlan &plan,
-                                             int level) {
+// What stays on the device for the whole batch
+struct RlcBatch {
+    fe *d_tab = nullptr, *d_tab_w = nullptr;          // product tables: hi scaled by r_j / by (j + 1) r_j
+    fe *d_partial = nullptr, *d_partial_w = nullptr;  // level-0 slices of the two scalar vectors
+    xyzz *d_scaled = nullptr, *d_scaled_w = nullptr;  // P_j, (j + 1) P_j
+    uint32_t n_slices0 = 0;
+    bool weighted = false;  // the *_w members are built (only after level 0 failed)
+};
+
+// One level of checks, ALL groups in one launch set.  status[g] as in k_locate.
+static std::vector<uint32_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab, const RlcBatch &rb,
+                                              const LevelPlan &plan, int level, bool locator) {
     const int field = ab.curve == 1 ? 0 : 1;
     CurveCtx &cc = c.curve[ab.curve];
     const uint32_t Gs = (uint32_t)plan.sliced.size(), Gc = (uint32_t)plan.combined.size(), Gm = Gs + Gc;
     const uint32_t Gd = (uint32_t)plan.derived.size(), G = Gm + Gd;
-    const uint32_t n_slices0 = (ab.m + COMBINE_SLICE - 1) / COMBINE_SLICE;
-    // one upload: slice ranges of the sliced groups (Gs + 1 entries are not enough: ranges need not be adjacent, so
-    // 2 per group) | combine subset | combine group offsets | P ranges of all groups (2 per group) | derived triples
+    const uint32_t nv = locator ? 2u : 1u;  // sums per group
+    // one upload: slice ranges of the sliced groups | combine subset | combine group offsets | ranges of all groups |
+    // derived triples
     std::vector<uint32_t> meta;
     const size_t o_sl = meta.size();
     for (auto &g : plan.sliced) {
@@ -400,14 +490,25 @@ static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers
     uint32_t *h_meta = sb.h_subset.reserve(meta.size());
     std::memcpy(h_meta, meta.data(), meta.size() * 4);
     uint32_t *d_meta = sb.d_subset.reserve(meta.size());
-    // XYZZ scratch: [A even | A odd | D], each ab.m long (groups are disjoint and non-empty: G <= m)
-    xyzz *d_x = sb.d_xyzz.reserve(3 * (size_t)ab.m);
-    xyzz *d_A = d_x + (size_t)(level & 1) * ab.m, *d_A_prev = d_x + (size_t)((level & 1) ^ 1) * ab.m, *d_D = d_x + 2 * (size_t)ab.m;
-    uint8_t *d_ok = reinterpret_cast<uint8_t *>(sb.d_out_can.reserve((G + 3) / 4 + 1));
-    fe *d_S = sb.d_S.reserve((size_t)std::max<uint32_t>(Gm, 1) << ab.k);
-    fe *d_partial = sb.d_partial.reserve((size_t)n_slices0 << ab.k);  // level-0 slices, kept for the whole batch
-    uint8_t *h_out = sb.h_out.reserve(G);
+    // XYZZ scratch, each array ab.m long (groups are disjoint and non-empty: G <= m):
+    //   A even [plain | weighted], A odd [plain | weighted], D [plain | weighted], raw MSM output [2 m]
+    const uint32_t stride = ab.m;
+    xyzz *d_x = sb.d_xyzz.reserve(8 * (size_t)ab.m);
+    xyzz *d_A = d_x + (size_t)(level & 1) * 2 * ab.m, *d_A_prev = d_x + (size_t)((level & 1) ^ 1) * 2 * ab.m;
+    xyzz *d_D = d_x + 4 * (size_t)ab.m, *d_raw = d_x + 6 * (size_t)ab.m;
+    uint32_t *d_status = sb.d_out_can.reserve(G);
+    uint32_t *h_status = sb.h_status.reserve(G);
+    fe *d_S = sb.d_S.reserve((size_t)std::max<uint32_t>(nv * Gm, 1) << ab.k);
     CTX_CUDA_OK(cudaMemcpyAsync(d_meta, h_meta, meta.size() * 4, cudaMemcpyHostToDevice, rs.s));
+    // commitment side on the auxiliary stream, beside the MSM
+    CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));
+    CTX_CUDA_OK(cudaStreamWaitEvent(rs.aux, rs.fork, 0));
+    if (ab.curve == 0)
+        k_range_sums<FpParams><<<dim3(G, nv), SUBSET_THREADS, 0, rs.aux>>>(rb.d_scaled, rb.d_scaled_w, d_meta + o_rng, d_D, stride);
+    else
+        k_range_sums<FqParams><<<dim3(G, nv), SUBSET_THREADS, 0, rs.aux>>>(rb.d_scaled, rb.d_scaled_w, d_meta + o_rng, d_D, stride);
+    CTX_CUDA_OK(cudaEventRecord(rs.join, rs.aux));
+    c.launches += 1;
     if (rs.timing) {
         if (!rs.ev[0]) {
             CTX_CUDA_OK(cudaEventCreate(&rs.ev[0]));
@@ -416,155 +517,209 @@ static std::vector<uint8_t> acc_check_groups(Context &c, AccRun &rs, SideBuffers
         CTX_CUDA_OK(cudaEventRecord(rs.ev[0], rs.s));
     }
     uint32_t combine_proofs = 0, combine_vectors = 0;
-    if (level == 0) {  // slices of the whole batch, in place (subset == nullptr: proof j is table j)
-        std::vector<uint32_t> soff(n_slices0 + 1);
-        for (uint32_t i = 0; i <= n_slices0; i++) soff[i] = std::min(ab.m, i * COMBINE_SLICE);
-        uint32_t *h_soff = sb.h_soff.reserve(soff.size());
-        std::memcpy(h_soff, soff.data(), soff.size() * 4);
-        uint32_t *d_soff = sb.d_soff.reserve(soff.size());
-        CTX_CUDA_OK(cudaMemcpyAsync(d_soff, h_soff, soff.size() * 4, cudaMemcpyHostToDevice, rs.s));
-        launch_bpoly_combine(field, sb.d_tab.p, nullptr, d_soff, n_slices0, ab.m, ab.k, d_partial, rs.s);
-        c.launches += 1;
-        combine_proofs += ab.m;
-        combine_vectors += n_slices0;
-    }
-    if (Gc) {
-        launch_bpoly_combine(field, sb.d_tab.p, d_meta + o_sub, d_meta + o_coff, Gc, nsub, ab.k, d_S + ((size_t)Gs << ab.k), rs.s);
-        c.launches += 1;
-        combine_proofs += nsub;
-        combine_vectors += Gc;
-    }
+    if (Gc)
+        for (uint32_t v = 0; v < nv; v++) {
+            launch_bpoly_combine(field, v ? rb.d_tab_w : rb.d_tab, d_meta + o_sub, d_meta + o_coff, Gc, nsub, ab.k,
+                                 d_S + ((size_t)(v * Gm + Gs) << ab.k), rs.s);
+            c.launches += 1;
+            combine_proofs += nsub;
+            combine_vectors += Gc;
+        }
     if (rs.timing) CTX_CUDA_OK(cudaEventRecord(rs.ev[1], rs.s));
-    if (Gs) {
-        dim3 grid(((1u << ab.k) + 255) / 256, Gs);
-        if (field == 0)
-            k_sum_slices<FpParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + o_sl, ab.k, d_S);
+    if (Gs)
+        for (uint32_t v = 0; v < nv; v++) {
+            dim3 grid(((1u << ab.k) + 255) / 256, Gs);
+            const fe *src = v ? rb.d_partial_w : rb.d_partial;
+            fe *dst = d_S + ((size_t)(v * Gm) << ab.k);
+            if (field == 0)
+                k_sum_slices<FpParams><<<grid, 256, 0, rs.s>>>(src, d_meta + o_sl, ab.k, dst);
+            else
+                k_sum_slices<FqParams><<<grid, 256, 0, rs.s>>>(src, d_meta + o_sl, ab.k, dst);
+            c.launches += 1;
+        }
+    if (Gm) {
+        cc.fixed->enable_kernel_timing(rs.timing);
+        cc.fixed->run_xyzz(reinterpret_cast<const uint32_t *>(d_S), nv * Gm, 1u << ab.k, d_raw, rs.s);
+        for (uint32_t v = 0; v < nv; v++)
+            CTX_CUDA_OK(cudaMemcpyAsync(d_A + (size_t)v * stride, d_raw + (size_t)v * Gm, (size_t)Gm * sizeof(xyzz), cudaMemcpyDeviceToDevice, rs.s));
+    }
+    if (Gd) {
+        if (ab.curve == 0)
+            k_derive_last_child<FpParams><<<dim3(Gd, nv), SUBSET_THREADS, 0, rs.s>>>(d_A_prev, d_A, d_meta + o_der, Gm, stride);
         else
-            k_sum_slices<FqParams><<<grid, 256, 0, rs.s>>>(d_partial, d_meta + o_sl, ab.k, d_S);
+            k_derive_last_child<FqParams><<<dim3(Gd, nv), SUBSET_THREADS, 0, rs.s>>>(d_A_prev, d_A, d_meta + o_der, Gm, stride);
         c.launches += 1;
     }
-    cc.fixed->enable_kernel_timing(rs.timing);
-    cc.fixed->run_xyzz(reinterpret_cast<const uint32_t *>(d_S), Gm, 1u << ab.k, d_A, rs.s);
-    if (rs.scaled_ready) {  // first level: the P_j come from the auxiliary stream
-        CTX_CUDA_OK(cudaStreamWaitEvent(rs.s, rs.scaled_ready, 0));
-        rs.scaled_ready = nullptr;
-    }
-    if (ab.curve == 0) {
-        k_range_sums<FpParams><<<G, SUBSET_THREADS, 0, rs.s>>>(sb.d_scaled.p, d_meta + o_rng, d_D);
-        if (Gd) k_derive_last_child<FpParams><<<Gd, SUBSET_THREADS, 0, rs.s>>>(d_A_prev, d_A, d_meta + o_der, Gm);
-        k_xyzz_pairs_equal<FpParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_A, d_D, G, d_ok);
-    } else {
-        k_range_sums<FqParams><<<G, SUBSET_THREADS, 0, rs.s>>>(sb.d_scaled.p, d_meta + o_rng, d_D);
-        if (Gd) k_derive_last_child<FqParams><<<Gd, SUBSET_THREADS, 0, rs.s>>>(d_A_prev, d_A, d_meta + o_der, Gm);
-        k_xyzz_pairs_equal<FqParams><<<(G + 127) / 128, 128, 0, rs.s>>>(d_A, d_D, G, d_ok);
-    }
-    c.launches += Gd ? 3 : 2;
-    CTX_CUDA_OK(cudaMemcpyAsync(h_out, d_ok, G, cudaMemcpyDeviceToHost, rs.s));
+    CTX_CUDA_OK(cudaStreamWaitEvent(rs.s, rs.join, 0));
+    if (ab.curve == 0)
+        k_locate<FpParams><<<G, LOCATE_THREADS, 0, rs.s>>>(d_A, d_D, stride, d_meta + o_rng, locator ? 1 : 0, d_status);
+    else
+        k_locate<FqParams><<<G, LOCATE_THREADS, 0, rs.s>>>(d_A, d_D, stride, d_meta + o_rng, locator ? 1 : 0, d_status);
+    c.launches += 1;
+    CTX_CUDA_OK(cudaMemcpyAsync(h_status, d_status, (size_t)G * 4, cudaMemcpyDeviceToHost, rs.s));
     uint32_t e = cc.fixed->take_error(rs.s);  // synchronises
     if (e) throw std::runtime_error("accumulator check: scalar overflow flagged by the MSM engine");
     if (rs.timing) {
         float ms = 0.f;
         CTX_CUDA_OK(cudaEventElapsedTime(&ms, rs.ev[0], rs.ev[1]));
         rs.stats.combine_ms += ms;
-        rs.stats.accumulate_ms += cc.fixed->last_accumulate_ms();
-        rs.stats.msm_points += (uint64_t)Gm << ab.k;
-        rs.stats.msm_count += Gm;
+        if (Gm) rs.stats.accumulate_ms += cc.fixed->last_accumulate_ms();
+        rs.stats.msm_points += (uint64_t)(nv * Gm) << ab.k;
+        rs.stats.msm_count += nv * Gm;
         rs.stats.combine_proofs += combine_proofs;
         rs.stats.combine_vectors += combine_vectors;
     }
-    std::vector<uint8_t> pass(G);
-    for (uint32_t g = 0; g < G; g++) pass[g] = h_out[g];
-    return pass;
+    return std::vector<uint32_t>(h_status, h_status + G);
 }
 
-// where a failing group [a, b) is cut: children in order; the last one is the derived child
-static std::vector<uint32_t> split_points(uint32_t a, uint32_t b) {
-    const uint32_t size = b - a;
-    std::vector<uint32_t> cuts;
-    if (size <= 4) {
-        for (uint32_t j = a + 1; j < b; j++) cuts.push_back(j);
-    } else if (size > 2 * COMBINE_SLICE) {
-        // halve at a slice boundary so that both children can be built from kept slices
-        uint32_t mid = a + size / 2;
-        mid = (mid + COMBINE_SLICE - 1) / COMBINE_SLICE * COMBINE_SLICE;
-        if (mid <= a || mid >= b) mid = a + size / 2;
-        cuts.push_back(mid);
-    } else {
-        cuts.push_back(a + (size + 1) / 2);
+// Level-0 slices of one scalar vector (subset == nullptr: proof j is table j)
+static void combine_slices(Context &c, AccRun &rs, SideBuffers &sb, const AccumulatorBatch &ab, const fe *d_tab, fe *d_partial,
+                           uint32_t n_slices0) {
+    const int field = ab.curve == 1 ? 0 : 1;
+    uint32_t *h_soff = sb.h_soff.reserve(n_slices0 + 1);
+    for (uint32_t i = 0; i <= n_slices0; i++) h_soff[i] = std::min(ab.m, i * COMBINE_SLICE);
+    uint32_t *d_soff = sb.d_soff.reserve(n_slices0 + 1);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_soff, h_soff, (size_t)(n_slices0 + 1) * 4, cudaMemcpyHostToDevice, rs.s));
+    if (rs.timing) {
+        if (!rs.ev[0]) {
+            CTX_CUDA_OK(cudaEventCreate(&rs.ev[0]));
+            CTX_CUDA_OK(cudaEventCreate(&rs.ev[1]));
+        }
+        CTX_CUDA_OK(cudaEventRecord(rs.ev[0], rs.s));
     }
+    launch_bpoly_combine(field, d_tab, nullptr, d_soff, n_slices0, ab.m, ab.k, d_partial, rs.s);
+    c.launches += 1;
+    if (rs.timing) {
+        CTX_CUDA_OK(cudaEventRecord(rs.ev[1], rs.s));
+        CTX_CUDA_OK(cudaEventSynchronize(rs.ev[1]));
+        float ms = 0.f;
+        CTX_CUDA_OK(cudaEventElapsedTime(&ms, rs.ev[0], rs.ev[1]));
+        rs.stats.combine_ms += ms;
+        rs.stats.combine_proofs += ab.m;
+        rs.stats.combine_vectors += n_slices0;
+    }
+}
+
+// children of an unresolved group [a, b): `t` parts, cut at slice boundaries while the parts are larger than a slice
+static std::vector<uint32_t> split_points(uint32_t a, uint32_t b, uint32_t t) {
+    const uint32_t size = b - a;
+    uint32_t part = (size + t - 1) / t;
+    if (part > COMBINE_SLICE) part = (part + COMBINE_SLICE - 1) / COMBINE_SLICE * COMBINE_SLICE;
+    std::vector<uint32_t> cuts;
+    uint32_t first = part;
+    if (part > COMBINE_SLICE && a % COMBINE_SLICE) first = part - a % COMBINE_SLICE;  // land on slice boundaries
+    for (uint32_t cut = a + first; cut < b; cut += part) cuts.push_back(cut);
+    if (cuts.empty()) cuts.push_back(a + (size + 1) / 2);
     return cuts;
 }
 
-// Group testing in levels: the whole batch first (the common case ends here: one combine + one MSM), then failing
-// groups are halved, every level being ONE batched launch set (~k log2(n/k) MSMs for k bad proofs of n).
-// A failing singleton is a bad proof: r != 0, so r*A == r*C <=> A == C.
+// Group testing in levels (see the block comment above LevelGroup).  The common case -- every proof good -- ends
+// after level 0: one combine + one MSM.
 static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab) {
     const int field = ab.curve == 1 ? 0 : 1;
     AccDevice dv = acc_prepare(c, rs, sb, ab);
     uint8_t *h_r = sb.h_r.reserve((size_t)ab.m * 32);
     for (uint32_t i = 0; i < ab.m; i++) random_128(h_r + 32 * (size_t)i);
-    fe *d_r_can = sb.d_r_can.reserve(ab.m), *d_r = sb.d_r.reserve(ab.m);
-    fe *d_tab = sb.d_tab.reserve((size_t)ab.m * BPOLY_TABLE);
+    fe *d_r_can = sb.d_r_can.reserve(ab.m), *d_r = sb.d_r.reserve(2 * (size_t)ab.m);
+    RlcBatch rb;
+    rb.n_slices0 = (ab.m + COMBINE_SLICE - 1) / COMBINE_SLICE;
+    rb.d_tab = sb.d_tab.reserve(2 * (size_t)ab.m * BPOLY_TABLE);
+    rb.d_tab_w = rb.d_tab + (size_t)ab.m * BPOLY_TABLE;
+    rb.d_partial = sb.d_partial.reserve((size_t)2 * rb.n_slices0 << ab.k);
+    rb.d_partial_w = rb.d_partial + ((size_t)rb.n_slices0 << ab.k);
+    rb.d_scaled = sb.d_scaled.reserve(2 * (size_t)ab.m);
+    rb.d_scaled_w = rb.d_scaled + ab.m;
     affine *d_pts = sb.d_pts.reserve(ab.m);
-    xyzz *d_scaled = sb.d_scaled.reserve(ab.m);
     uint32_t *d_bad = sb.d_bad.reserve(1);
     uint32_t *h_bad = sb.h_bad.reserve(1);
     CTX_CUDA_OK(cudaMemcpyAsync(d_r_can, h_r, (size_t)ab.m * 32, cudaMemcpyHostToDevice, rs.s));
     CTX_CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, rs.s));
     launch_affine_to_mont_checked(ab.curve, dv.d_pts_can, d_pts, ab.m, d_bad, rs.s);
     CTX_CUDA_OK(cudaMemcpyAsync(h_bad, d_bad, 4, cudaMemcpyDeviceToHost, rs.s));
-    // P_j = r_j C_j beside the rest of level 0
+    // P_j = r_j C_j beside the tables and the combine of level 0 (the first k_range_sums is queued behind it)
     CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));
     CTX_CUDA_OK(cudaStreamWaitEvent(rs.aux, rs.fork, 0));
     if (ab.curve == 0)
-        k_scale_points_128<FpParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(d_pts, d_r_can, ab.m, d_scaled);
+        k_scale_points_128<FpParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(d_pts, d_r_can, ab.m, rb.d_scaled);
     else
-        k_scale_points_128<FqParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(d_pts, d_r_can, ab.m, d_scaled);
-    CTX_CUDA_OK(cudaEventRecord(rs.join, rs.aux));
-    rs.scaled_ready = rs.join;
+        k_scale_points_128<FqParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(d_pts, d_r_can, ab.m, rb.d_scaled);
     launch_fe_to_mont(field, d_r_can, d_r, ab.m, rs.s);
-    launch_bpoly_tables(field, sb.d_chal.p, d_tab, ab.m, ab.k, d_r, false, rs.s);
+    launch_bpoly_tables(field, sb.d_chal.p, rb.d_tab, ab.m, ab.k, d_r, false, rs.s);
     c.launches += 4;
+    combine_slices(c, rs, sb, ab, rb.d_tab, rb.d_partial, rb.n_slices0);
+
     LevelPlan plan;
-    plan.sliced.resize(1);
-    plan.sliced[0].a = 0;
-    plan.sliced[0].b = ab.m;
+    plan.sliced.push_back(LevelGroup{0, ab.m, 0});
+    bool locator = false;
     for (int level = 0; plan.size(); level++) {
-        std::vector<uint8_t> pass = acc_check_groups(c, rs, sb, ab, plan, level);
+        std::vector<uint32_t> status = acc_check_groups(c, rs, sb, ab, rb, plan, level, locator);
         // the stream has drained: the on-curve flag of the batch's points is on the host
         if (level == 0 && *h_bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
         LevelPlan next;
+        if (!locator) {  // level 0
+            if (status[0] == 1) {
+                for (uint32_t i = 0; i < ab.m; i++) ab.ok[i] = 1;
+                return;
+            }
+            // something is bad: build the locator-weighted twins once, then test the whole batch again with both sums
+            if (ab.curve == 0) {
+                k_weight_points<FpParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(rb.d_scaled, ab.m, rb.d_scaled_w);
+                k_weight_scalars<FqParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_r, ab.m, d_r + ab.m);
+            } else {
+                k_weight_points<FqParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(rb.d_scaled, ab.m, rb.d_scaled_w);
+                k_weight_scalars<FpParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_r, ab.m, d_r + ab.m);
+            }
+            launch_bpoly_tables(field, sb.d_chal.p, rb.d_tab_w, ab.m, ab.k, d_r + ab.m, false, rs.s);
+            c.launches += 3;
+            combine_slices(c, rs, sb, ab, rb.d_tab_w, rb.d_partial_w, rb.n_slices0);
+            rb.weighted = true;
+            locator = true;
+            next.sliced.push_back(LevelGroup{0, ab.m, 0});
+            plan = std::move(next);
+            continue;
+        }
+        // verdicts; unresolved groups are split next
+        std::vector<uint32_t> open;
+        for (size_t g = 0; g < plan.size(); g++) {
+            const LevelGroup &grp = plan.at(g);
+            if (status[g] == 1) {
+                for (uint32_t i = grp.a; i < grp.b; i++) ab.ok[i] = 1;
+            } else if (status[g] >= 2) {
+                const uint32_t bad = status[g] - 2;
+                if (bad < grp.a || bad >= grp.b) throw std::runtime_error("accumulator check: locator returned an index outside its group");
+                for (uint32_t i = grp.a; i < grp.b; i++) ab.ok[i] = i == bad ? 0 : 1;
+            } else if (grp.size() <= 2) {
+                for (uint32_t i = grp.a; i < grp.b; i++) ab.ok[i] = 0;  // not "none" and not "exactly one": every member is bad
+            } else {
+                open.push_back((uint32_t)g);
+            }
+        }
+        if (open.empty()) break;
+        const uint32_t t = std::max<uint32_t>(2, std::min<uint32_t>(SPLIT_TARGET, (SPLIT_TARGET + (uint32_t)open.size() - 1) / (uint32_t)open.size()));
         struct Pending {
             uint32_t parent, list, begin, end;  // siblings [begin, end) inside list 0 (sliced) or 1 (combined)
         };
         std::vector<Pending> pend;
-        for (size_t g = 0; g < plan.size(); g++) {
+        for (uint32_t g : open) {
             const LevelGroup &grp = plan.at(g);
-            if (pass[g]) {
-                for (uint32_t i = grp.a; i < grp.b; i++) ab.ok[i] = 1;
-            } else if (grp.size() == 1) {
-                ab.ok[grp.a] = 0;
-            } else {
-                std::vector<uint32_t> cuts = split_points(grp.a, grp.b);
-                // the MSM children of one parent all go to the same list so that they stay adjacent
-                bool all_sliced = true;
-                uint32_t lo = grp.a;
-                for (uint32_t cut : cuts) {
-                    LevelGroup child{lo, cut, (uint32_t)g};
-                    all_sliced = all_sliced && slice_aligned(child, ab.m);
-                    lo = cut;
-                }
-                std::vector<LevelGroup> &list = all_sliced ? next.sliced : next.combined;
-                Pending pd{(uint32_t)g, all_sliced ? 0u : 1u, (uint32_t)list.size(), 0};
-                lo = grp.a;
-                for (uint32_t cut : cuts) {
-                    list.push_back(LevelGroup{lo, cut, (uint32_t)g});
-                    lo = cut;
-                }
-                pd.end = (uint32_t)list.size();
-                pend.push_back(pd);
-                next.derived.push_back(LevelGroup{lo, grp.b, (uint32_t)g});
+            std::vector<uint32_t> cuts = split_points(grp.a, grp.b, std::min(t, grp.size()));
+            // the MSM children of one parent all go to the same list so that they stay adjacent
+            bool all_sliced = true;
+            uint32_t lo = grp.a;
+            for (uint32_t cut : cuts) {
+                all_sliced = all_sliced && slice_aligned(LevelGroup{lo, cut, g}, ab.m);
+                lo = cut;
             }
+            std::vector<LevelGroup> &list = all_sliced ? next.sliced : next.combined;
+            Pending pd{g, all_sliced ? 0u : 1u, (uint32_t)list.size(), 0};
+            lo = grp.a;
+            for (uint32_t cut : cuts) {
+                list.push_back(LevelGroup{lo, cut, g});
+                lo = cut;
+            }
+            pd.end = (uint32_t)list.size();
+            pend.push_back(pd);
+            next.derived.push_back(LevelGroup{lo, grp.b, g});
         }
         for (const Pending &pd : pend) {
             const uint32_t shift = pd.list ? (uint32_t)next.sliced.size() : 0u;
