@@ -162,6 +162,29 @@ def test_rlc_batch_returns_exactly_the_per_proof_bits(gpu):
     assert gpu.accumulator_check([], gpu.MODE_RLC) == []
 
 
+@pytest.mark.parametrize("n", [130, 333])
+def test_group_testing_patterns(gpu, n):
+    """The locator / splitting logic of the batched check on batches that are not a multiple of the slice size,
+    with the corruption patterns that stress it: exactly one bad proof (first, last, middle: resolved by the
+    single-error locator), two identical bad proofs in one slice, neighbours across a slice boundary, a whole
+    slice bad, every other proof bad, everything bad.  Expected bits are known by construction."""
+    proof = golden("mina_state.proof")
+    bad_w = _flip(proof, OFF_WRAP_PRECHAL + 9, 3)          # wrap accumulator wrong
+    bad_s = _flip(proof, OFF_STEP_PRECHAL + 240 + 31, 1)   # second step accumulator wrong
+    patterns = {
+        "single first": {0: bad_w}, "single last": {n - 1: bad_w}, "single middle": {n // 2: bad_s},
+        "two identical in one slice": {5: bad_w, 6: bad_w}, "across a slice boundary": {63: bad_w, 64: bad_w, 65: bad_s},
+        "one per family": {70: bad_w, 71: bad_s},
+        "whole slice": {i: bad_w for i in range(64, 128)},
+        "every other": {i: (bad_w if i % 4 else bad_s) for i in range(0, n, 2)},
+        "all": {i: bad_w for i in range(n)},
+    }
+    for name, bad in patterns.items():
+        batch = [bad.get(i, proof) for i in range(n)]
+        want = [(0, 1, 1) if batch[i] is bad_w else (1, 1, 0) if batch[i] is bad_s else (1, 1, 1) for i in range(n)]
+        assert gpu.accumulator_check(gpu.Batch(batch), gpu.MODE_RLC) == want, name
+
+
 # ---- the boundary with a device present -------------------------------------------------------------------------------
 def test_state_ffi_runs_every_built_stage_and_still_refuses_a_partial_accept(gpu):
     S = gpu.STAGES
