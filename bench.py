@@ -76,6 +76,20 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
 
 
+def ncu_capture(kernel):
+    """DRAM traffic and pipe counters of `kernel` from the committed `ncu --set full` capture of this same command's
+    profile step (profiles/r2_rlc_step_kernels.json, made by tools/ncu_raw_summary.py).  None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_rlc_step_kernels.json")))["kernels"]
+    except Exception:
+        return None
+    hit = [v for k, v in d.items() if k.startswith(kernel + "<") and v["launches"] >= 2] or [v for k, v in d.items() if k.startswith(kernel + "<")]
+    return max(hit, key=lambda v: v["ms"]) if hit else None
+
+
+MODMUL_CEILING = 7.31e10  # dependent-chain Montgomery products per second, all SMs, measured (DESIGN.md 3.1, tools/lab/accum_lab.cu)
+
+
 def golden(name):
     return open(os.path.join(ROOT, "tests", "golden", name), "rb").read()
 
@@ -305,10 +319,21 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
                "algorithmic_bytes_per_step": ALG_BYTES_PER_POINT * pts,
                "note": "96 B x MSM points / summed k_accumulate CUDA-event time; integer-issue-bound: %.3g modmul/s (10 per mixed add, 16 adds per point)" % (160 * pts / (acc_ms * 1e-3) if acc_ms else 0)}
         acc["frac"] = acc["achieved"] / peak
+        cap = ncu_capture("k_accumulate")
+        if cap:  # per launch, like `achieved`: the capture's DRAM bytes over its launches of this kernel
+            acc["traffic"] = (cap["dram_read_bytes"] + cap["dram_write_bytes"]) / cap["launches"]
+            acc["traffic_note"] = "ncu --set full of `bench.py --profile-step rlc`: %d launches, %.0f MB read + %.0f MB written; L2 hit %.0f %%; fmaheavy pipe busy %.0f %%" % (
+                cap["launches"], cap["dram_read_bytes"] / 1e6, cap["dram_write_bytes"] / 1e6, cap["l2_hit_pct"], cap["fmaheavy_busy_pct"])
+        mm = 160 * pts / (acc_ms * 1e-3) if acc_ms else 0.0
+        acc["int_pipe"] = {"bound": "int32 multiply pipe (fmaheavy)", "achieved": mm, "peak": MODMUL_CEILING, "unit": "modmul/s", "frac": mm / MODMUL_CEILING,
+                           "note": "10 Montgomery products per mixed addition x 16 additions per point; peak = measured dependent-chain ceiling of mul_ptx2"}
         comb = {"bound": "hbm", "achieved": comb_bytes / (comb_ms * 1e-3) / 1e9 if comb_ms else 0.0, "peak": peak, "unit": "GB/s", "traffic": None,
                 "kernel": "k_bpoly_combine", "peak_source": which, "ms_per_step_in_kernel": comb_ms, "algorithmic_bytes_per_step": comb_bytes,
                 "note": "integer-issue-bound: %.3g modmul/s" % (comb_mod / (comb_ms * 1e-3) if comb_ms else 0)}
         comb["frac"] = comb["achieved"] / peak
+        cap = ncu_capture("k_bpoly_combine")
+        if cap:
+            comb["traffic"] = (cap["dram_read_bytes"] + cap["dram_write_bytes"]) / cap["launches"]
         return acc, comb
 
     acc_rlc, comb_rlc = kernel_lines(kms, a.steps)
