@@ -33,8 +33,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH = 1024              # proofs per step, whole job (BASELINE.json configs[3] / north_star target)
-N_CORRUPT = 10            # 1 % of the batch gets one flipped prechallenge bit, at seeded random positions
+BATCH = 1024              # proofs per step, whole job (BASELINE.json configs[3] / north_star target); --batch overrides
+N_CORRUPT = 10            # 1 % of the batch gets one flipped prechallenge bit, at seeded random positions; --corrupt overrides
 CORRUPT_SEED = 0x4D494E41
 ALG_BYTES_PER_POINT = 96  # 64 B affine base + 32 B scalar
 OFF_WRAP_PRE, OFF_WRAP_X, OFF_WRAP_Y = 73, 374, 414
@@ -94,13 +94,13 @@ def golden(name):
     return open(os.path.join(ROOT, "tests", "golden", name), "rb").read()
 
 
-def corrupt_positions(n_corrupt=N_CORRUPT):
+def corrupt_positions(n_corrupt=None):
     import random
 
-    return set(random.Random(CORRUPT_SEED).sample(range(BATCH), n_corrupt))
+    return set(random.Random(CORRUPT_SEED).sample(range(BATCH), N_CORRUPT if n_corrupt is None else n_corrupt))
 
 
-def synth_batch(n_corrupt=N_CORRUPT):
+def synth_batch(n_corrupt=None):
     """The fixed 1024-proof batch: (proofs, pubs, expected built-stage bit)."""
     proof, pub = golden("mina_state.proof"), golden("mina_state.pub")
     bad = corrupt_positions(n_corrupt)
@@ -192,7 +192,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u256 modular (4x64 Montgomery)", "data": "synthetic",
-        "config": {"workload": "state1024: the same 1024-proof batch, per-proof accumulator MSMs like the reference (verify_block per proof)",
+        "config": {"workload": "state%d: the same batch, per-proof accumulator MSMs like the reference (verify_block per proof)" % BATCH,
                    "built_stages": BUILT, "absent_stages": ABSENT},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "modmul_ns": modmul_ns,
                          "sample": "%d proofs per step out of the 1024-proof batch; C restatement of arkworks' bucket MSM (oracle/pasta_ref.c, c = ln n + 2, one thread per window, unrolled 4x64 CIOS) + Python bincode decoder; NOT the reference binary (no Rust toolchain); arkworks+asm is usually quoted at 20-25 ns per modmul vs modmul_ns here" % sample},
@@ -349,7 +349,7 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
         "metric": METRIC, "value": BATCH * a.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
         "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u256 modular (8x32 Montgomery)", "data": "synthetic",
-        "config": {"workload": "state1024: 1024 serialized proof-of-state inputs per step (reference fixture x1024, 10 at seeded random positions with a flipped prechallenge bit; `other_batches` = none / one corrupted), rank r takes i = r mod N, one NCCL all-reduce(MIN) of 1024 result bytes per step",
+        "config": {"workload": "state%d: serialized proof-of-state inputs, one batch per step (reference fixture x%d, %d at seeded random positions with a flipped prechallenge bit; `other_batches` = none / one corrupted), rank r takes i = r mod N, one NCCL all-reduce(MIN) of the result bytes per step" % (BATCH, BATCH, N_CORRUPT),
                    "mode": "rlc (random linear combination over the shard + bisection; per-proof numbers in `per_proof_mode`)",
                    "built_stages": BUILT, "absent_stages": ABSENT,
                    "l2": "per-step working set: %d x 16 KiB product tables + 64 MiB / 32 MiB fixed-base tables > 126 MB L2 together; inputs differ per proof only in 10 members" % (3 * m)},
@@ -457,6 +457,7 @@ def bench_msm20(a, torch, dist, mb, rank, world, dev):
 
 
 def main():
+    global BATCH, N_CORRUPT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -465,7 +466,11 @@ def main():
     ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20"])
     ap.add_argument("--profile-step", default="", choices=["", "rlc", "per_proof"],
                     help="run one extra untimed step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off)")
+    ap.add_argument("--batch", type=int, default=BATCH, help="proofs per step (default: the 1024 of BASELINE.json; 64 = configs[2])")
+    ap.add_argument("--corrupt", type=int, default=-1, help="corrupted members (default: 1 %% of the batch)")
     a = ap.parse_args()
+    BATCH = a.batch
+    N_CORRUPT = a.corrupt if a.corrupt >= 0 else max(1, round(BATCH / 100)) if BATCH != 1024 else N_CORRUPT
     if a.impl == "reference":
         return run_reference(a)
 

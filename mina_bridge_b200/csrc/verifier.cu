@@ -425,7 +425,15 @@ static __global__ void __launch_bounds__(LOCATE_THREADS) k_locate(const xyzz *__
 // groups are open, so the launch set fills the GPU; at slice boundaries while groups are large).  The last
 // child of every split needs no MSM (A_last = A_parent - siblings).
 static constexpr uint32_t COMBINE_SLICE = 64;
-static constexpr uint32_t SPLIT_TARGET = 16;  // open groups x children per level the splits aim for
+// open groups x children per level the splits aim for (MINA_B200_SPLIT_TARGET overrides it: tuning only)
+static uint32_t split_target() {
+    static const uint32_t v = [] {
+        const char *e = std::getenv("MINA_B200_SPLIT_TARGET");
+        int x = e ? std::atoi(e) : 0;
+        return (uint32_t)(x >= 2 && x <= 64 ? x : 4);  // 4: best of {2..32} on 1024/10, 128/2, 1024/30, 1024/100 (tools/sweep_split.sh)
+    }();
+    return v;
+}
 struct LevelGroup {
     uint32_t a = 0, b = 0;
     uint32_t parent = 0;  // index into the previous level's group list
@@ -695,7 +703,8 @@ static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &a
             }
         }
         if (open.empty()) break;
-        const uint32_t t = std::max<uint32_t>(2, std::min<uint32_t>(SPLIT_TARGET, (SPLIT_TARGET + (uint32_t)open.size() - 1) / (uint32_t)open.size()));
+        const uint32_t target = split_target();
+        const uint32_t t = std::max<uint32_t>(2, std::min<uint32_t>(target, (target + (uint32_t)open.size() - 1) / (uint32_t)open.size()));
         struct Pending {
             uint32_t parent, list, begin, end;  // siblings [begin, end) inside list 0 (sliced) or 1 (combined)
         };
