@@ -156,6 +156,28 @@ int mina_b200_bpoly_eval(int field, uint32_t nproofs, uint32_t npts, int k, cons
 int mina_b200_combined_inner_product(int field, uint32_t nproofs, uint32_t npolys, uint32_t npts, const uint8_t *evals32,
                                       const uint8_t *scales32, uint8_t *out32);
 
+/* ---- a9: batched IPA final check (poly-commitment SRS::verify) -------------------------------------------- */
+/* n openings over `curve`, all with the same number of rounds k (8 <= k <= 16, 2^k <= the resident SRS depth: the
+ * bases are g[0..2^k) and h), commitments and evaluation points.  Host buffers, canonical little-endian:
+ *   sponge_state96 [n][3] base-field elements + the sponge mode shared by the batch (0 = Absorbed(count), 1 =
+ *   Squeezed(count)): the Fq-sponge exactly as kimchi hands it over (`fq_sponge_before_evaluations`);
+ *   cip32, polyscale32, evalscale32, z1_32, z2_32 [n] scalars; eval_points32 [n][n_points]; delta64, sg64 [n];
+ *   commitments64 [n][n_comm]; lr64 [n][k][2] (L then R).
+ * poseidon_table: 174 x 32 bytes for the curve's BASE field (see the K3 section; table-driven, unpinned).
+ * ok[i] = 1 iff opening i verifies.  Openings are batched with per-opening 128-bit randomisers and the group
+ * testing of the accumulator checks; a non-canonical input or an off-curve point rejects that opening only. */
+typedef struct {
+    uint32_t n, rounds, n_comm, n_points;
+    uint32_t sponge_mode, sponge_count;
+    const uint8_t *sponge_state96;
+    const uint8_t *cip32, *polyscale32, *evalscale32, *z1_32, *z2_32;
+    const uint8_t *eval_points32;
+    const uint8_t *delta64, *sg64;
+    const uint8_t *commitments64;
+    const uint8_t *lr64;
+} mina_b200_ipa_batch;
+int mina_b200_ipa_verify(int curve, const uint8_t *poseidon_table, const mina_b200_ipa_batch *batch, uint8_t *ok);
+
 /* ---- K3: Poseidon (table-driven; see csrc/poseidon.hpp for the parity status of the constants) ------- */
 /* table = 174 x 32 bytes (MDS row-major, then 55 x 3 round constants).  states: n x 96 bytes, in place. */
 int mina_b200_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96);

@@ -31,6 +31,7 @@
 #include "consensus.hpp"
 #include "context.cuh"
 #include "ipa.cuh"
+#include "ipa_verify.cuh"
 #include "poseidon.cuh"
 #include "sol_account.hpp"
 #include "wire.hpp"
@@ -47,8 +48,18 @@ struct SideBuffers {  // one accumulator family (Vesta k=16 or Pallas k=15)
     DevBuf<affine> d_pts, d_res;
     DevBuf<xyzz> d_xyzz, d_scaled;
 };
+struct IpaBuffers {  // the batched IPA final check (one per curve)
+    PinnedBuf<uint8_t> h_in, h_t, h_pts;
+    DevBuf<uint8_t> d_in;
+    DevBuf<fe> d_tab, d_t, d_chal, d_chal_c, d_rand, d_scalars;
+    DevBuf<uint4> d_pre;
+    DevBuf<uint32_t> d_pts_can;
+    DevBuf<affine> d_pts;
+    DevBuf<xyzz> d_terms;
+};
 struct VerifierState {
     SideBuffers side[2];  // index = curve id: 0 Pallas (step accumulators), 1 Vesta (wrap accumulator)
+    IpaBuffers ipa[2];
     // Merkle fold
     DevBuf<MerkleNodeDev> d_nodes;
     DevBuf<uint32_t> d_depths;
@@ -73,6 +84,7 @@ static VerifierState &vstate() {
 }
 
 // ---- small host helpers ------------------------------------------------------------------------------
+static void parallel_for(size_t n, const std::function<void(size_t)> &fn);
 template <class F>
 static bool canonical(const wire::B32 &b, host::Fe<F> &out) {
     return host::Fe<F>::from_bytes_le(b.data(), out);
@@ -621,6 +633,18 @@ static std::vector<uint32_t> split_points(uint32_t a, uint32_t b, uint32_t t) {
     return cuts;
 }
 
+static void rlc_levels(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab, RlcBatch &rb, const fe *d_chal, fe *d_r,
+                       const uint32_t *h_bad);
+static void rlc_buffers(SideBuffers &sb, const AccumulatorBatch &ab, RlcBatch &rb) {
+    rb.n_slices0 = (ab.m + COMBINE_SLICE - 1) / COMBINE_SLICE;
+    rb.d_tab = sb.d_tab.reserve(2 * (size_t)ab.m * BPOLY_TABLE);
+    rb.d_tab_w = rb.d_tab + (size_t)ab.m * BPOLY_TABLE;
+    rb.d_partial = sb.d_partial.reserve((size_t)2 * rb.n_slices0 << ab.k);
+    rb.d_partial_w = rb.d_partial + ((size_t)rb.n_slices0 << ab.k);
+    rb.d_scaled = sb.d_scaled.reserve(2 * (size_t)ab.m);
+    rb.d_scaled_w = rb.d_scaled + ab.m;
+}
+
 // Group testing in levels (see the block comment above LevelGroup).  The common case -- every proof good -- ends
 // after level 0: one combine + one MSM.
 static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab) {
@@ -630,13 +654,7 @@ static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &a
     for (uint32_t i = 0; i < ab.m; i++) random_128(h_r + 32 * (size_t)i);
     fe *d_r_can = sb.d_r_can.reserve(ab.m), *d_r = sb.d_r.reserve(2 * (size_t)ab.m);
     RlcBatch rb;
-    rb.n_slices0 = (ab.m + COMBINE_SLICE - 1) / COMBINE_SLICE;
-    rb.d_tab = sb.d_tab.reserve(2 * (size_t)ab.m * BPOLY_TABLE);
-    rb.d_tab_w = rb.d_tab + (size_t)ab.m * BPOLY_TABLE;
-    rb.d_partial = sb.d_partial.reserve((size_t)2 * rb.n_slices0 << ab.k);
-    rb.d_partial_w = rb.d_partial + ((size_t)rb.n_slices0 << ab.k);
-    rb.d_scaled = sb.d_scaled.reserve(2 * (size_t)ab.m);
-    rb.d_scaled_w = rb.d_scaled + ab.m;
+    rlc_buffers(sb, ab, rb);
     affine *d_pts = sb.d_pts.reserve(ab.m);
     uint32_t *d_bad = sb.d_bad.reserve(1);
     uint32_t *h_bad = sb.h_bad.reserve(1);
@@ -652,8 +670,18 @@ static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &a
     else
         k_scale_points_128<FqParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(d_pts, d_r_can, ab.m, rb.d_scaled);
     launch_fe_to_mont(field, d_r_can, d_r, ab.m, rs.s);
-    launch_bpoly_tables(field, sb.d_chal.p, rb.d_tab, ab.m, ab.k, d_r, false, rs.s);
-    c.launches += 4;
+    c.launches += 3;
+    rlc_levels(c, rs, sb, ab, rb, sb.d_chal.p, d_r, h_bad);
+}
+
+// The levels themselves, shared by the accumulator checks and the IPA final checks: item j contributes
+// r_j * <b_poly_coefficients(chal_j), G[0..2^k)> on the g side (d_r: Montgomery, 2 m entries, the second half is
+// scratch for the locator weights) and P_j on the other (rb.d_scaled, complete or in flight on rs.aux).
+static void rlc_levels(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab, RlcBatch &rb, const fe *d_chal, fe *d_r,
+                       const uint32_t *h_bad) {
+    const int field = ab.curve == 1 ? 0 : 1;
+    launch_bpoly_tables(field, d_chal, rb.d_tab, ab.m, ab.k, d_r, false, rs.s);
+    c.launches += 1;
     combine_slices(c, rs, sb, ab, rb.d_tab, rb.d_partial, rb.n_slices0);
 
     LevelPlan plan;
@@ -662,7 +690,7 @@ static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &a
     for (int level = 0; plan.size(); level++) {
         std::vector<uint32_t> status = acc_check_groups(c, rs, sb, ab, rb, plan, level, locator);
         // the stream has drained: the on-curve flag of the batch's points is on the host
-        if (level == 0 && *h_bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
+        if (level == 0 && h_bad && *h_bad) throw std::runtime_error("accumulator check: a commitment is not a canonical curve point (callers validate first)");
         LevelPlan next;
         if (!locator) {  // level 0
             if (status[0] == 1) {
@@ -677,7 +705,7 @@ static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &a
                 k_weight_points<FqParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(rb.d_scaled, ab.m, rb.d_scaled_w);
                 k_weight_scalars<FpParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_r, ab.m, d_r + ab.m);
             }
-            launch_bpoly_tables(field, sb.d_chal.p, rb.d_tab_w, ab.m, ab.k, d_r + ab.m, false, rs.s);
+            launch_bpoly_tables(field, d_chal, rb.d_tab_w, ab.m, ab.k, d_r + ab.m, false, rs.s);
             c.launches += 3;
             combine_slices(c, rs, sb, ab, rb.d_tab_w, rb.d_partial_w, rb.n_slices0);
             rb.weighted = true;
@@ -736,6 +764,136 @@ static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &a
         }
         plan = std::move(next);
     }
+}
+
+// ---- batched IPA final check ------------------------------------------------------------------
+// Host: validation, packing, U = to_group(t) (group map with the exact Tonelli-Shanks root, srs.hpp).  Device: the
+// Fq-sponge transcript, endo challenges, scalars, the per-opening point sums B_i, and the group testing of the
+// accumulator checks on   sgrb_i * <b_poly_coefficients(chal_i), G[0..2^k)> + B_i == 0.
+template <class F, class S, bool SCALAR_LARGER>
+static void ipa_verify_t(Context &c, int curve, const poseidon::Params<F> &table, const mina_b200_ipa_batch &b, uint8_t *ok) {
+    using E = host::Fe<F>;
+    using ES = host::Fe<S>;
+    const uint32_t n_all = b.n, k = b.rounds, nc = b.n_comm, npts = b.n_points;
+    const uint32_t npp = 2 * k + nc + 4;
+    std::memset(ok, 0, n_all);
+    // host validation: canonical field elements, points on the curve ((0,0) = identity allowed for commitments only)
+    std::vector<uint8_t> valid(n_all, 1);
+    auto point_ok = [](const uint8_t *p, bool allow_identity) {
+        host::Affine<F> a;
+        if (!E::from_bytes_le(p, a.x) || !E::from_bytes_le(p + 32, a.y)) return false;
+        if (a.x.is_zero() && a.y.is_zero()) return allow_identity;
+        a.inf = false;
+        return a.on_curve();
+    };
+    parallel_for(n_all, [&](size_t i) {
+        bool good = true;
+        E tmp;
+        ES ts;
+        for (int q = 0; q < 3; q++) good = good && E::from_bytes_le(b.sponge_state96 + 96 * i + 32 * q, tmp);
+        for (const uint8_t *arr : {b.cip32, b.polyscale32, b.evalscale32, b.z1_32, b.z2_32}) good = good && ES::from_bytes_le(arr + 32 * i, ts);
+        for (uint32_t t = 0; t < npts; t++) good = good && ES::from_bytes_le(b.eval_points32 + 32 * (i * npts + t), ts);
+        good = good && point_ok(b.delta64 + 64 * i, false) && point_ok(b.sg64 + 64 * i, false);
+        for (uint32_t j = 0; j < 2 * k && good; j++) good = point_ok(b.lr64 + 64 * (i * 2 * k + j), false);
+        for (uint32_t m = 0; m < nc && good; m++) good = point_ok(b.commitments64 + 64 * (i * nc + m), true);
+        valid[i] = good;
+    });
+    std::vector<uint32_t> idx;
+    for (uint32_t i = 0; i < n_all; i++)
+        if (valid[i]) idx.push_back(i);
+    const uint32_t n = (uint32_t)idx.size();
+    if (!n) return;
+
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    AccRun rs;
+    setup_run(c, rs, 0, false);
+    IpaBuffers &ib = vstate().ipa[curve];
+    SideBuffers &sb = vstate().side[curve];
+    const int sfield = curve == 1 ? 0 : 1;  // scalar field id
+    // packed input, all 32-byte words: state[3n] | cip[n] | lr[4kn] | delta[2n] | z1 | z2 | polyscale | evalscale | elm[npts n] | rb | sgrb
+    const size_t w_state = 0, w_cip = w_state + 3 * (size_t)n, w_lr = w_cip + n, w_delta = w_lr + 4 * (size_t)k * n, w_z1 = w_delta + 2 * (size_t)n,
+                 w_z2 = w_z1 + n, w_ps = w_z2 + n, w_es = w_ps + n, w_elm = w_es + n, w_rb = w_elm + (size_t)npts * n, w_sg = w_rb + n,
+                 w_end = w_sg + n;
+    uint8_t *h_in = ib.h_in.reserve(32 * w_end);
+    for (uint32_t t = 0; t < n; t++) {
+        const size_t i = idx[t];
+        std::memcpy(h_in + 32 * (w_state + 3 * t), b.sponge_state96 + 96 * i, 96);
+        std::memcpy(h_in + 32 * (w_cip + t), b.cip32 + 32 * i, 32);
+        std::memcpy(h_in + 32 * (w_lr + 4 * (size_t)k * t), b.lr64 + 64 * (i * 2 * k), 128 * (size_t)k);
+        std::memcpy(h_in + 32 * (w_delta + 2 * t), b.delta64 + 64 * i, 64);
+        std::memcpy(h_in + 32 * (w_z1 + t), b.z1_32 + 32 * i, 32);
+        std::memcpy(h_in + 32 * (w_z2 + t), b.z2_32 + 32 * i, 32);
+        std::memcpy(h_in + 32 * (w_ps + t), b.polyscale32 + 32 * i, 32);
+        std::memcpy(h_in + 32 * (w_es + t), b.evalscale32 + 32 * i, 32);
+        std::memcpy(h_in + 32 * (w_elm + (size_t)npts * t), b.eval_points32 + 32 * (i * npts), 32 * (size_t)npts);
+        random_128(h_in + 32 * (w_rb + t));
+        random_128(h_in + 32 * (w_sg + t));
+    }
+    const fe *d_in = reinterpret_cast<const fe *>(ib.d_in.reserve(32 * w_end));
+    CTX_CUDA_OK(cudaMemcpyAsync(ib.d_in.p, h_in, 32 * w_end, cudaMemcpyHostToDevice, rs.s));
+    auto tab = table.device_table();
+    fe *d_tab = ib.d_tab.reserve(POSEIDON_TABLE_WORDS);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, rs.s));
+    fe *d_t = ib.d_t.reserve(n);
+    uint4 *d_pre = ib.d_pre.reserve((size_t)n * (k + 1));
+    k_ipa_transcript<F, S, SCALAR_LARGER><<<(4 * n + 127) / 128, 128, 0, rs.s>>>(d_in + w_state, b.sponge_mode, b.sponge_count, d_in + w_cip, d_in + w_lr,
+                                                                             d_in + w_delta, n, (int)k, d_tab, d_t, d_pre, d_pre + (size_t)n * k);
+    uint8_t *h_t = ib.h_t.reserve(32 * (size_t)n);
+    CTX_CUDA_OK(cudaMemcpyAsync(h_t, d_t, 32 * (size_t)n, cudaMemcpyDeviceToHost, rs.s));
+    CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));  // t is on the host once this event has fired
+    // everything that does not need U runs while the host maps t to the curve
+    fe *d_chal = ib.d_chal.reserve((size_t)n * k), *d_chal_c = ib.d_chal_c.reserve(n);
+    launch_endo_to_field(sfield, d_pre, d_chal, n * k, rs.s);
+    launch_endo_to_field(sfield, d_pre + (size_t)n * k, d_chal_c, n, rs.s);
+    fe *d_rand = ib.d_rand.reserve(2 * (size_t)n);  // rb | sgrb, Montgomery
+    launch_fe_to_mont(sfield, d_in + w_rb, d_rand, 2 * n, rs.s);
+    fe *d_scalars = ib.d_scalars.reserve((size_t)n * npp);
+    k_ipa_scalars<S><<<(n + 63) / 64, 64, 0, rs.s>>>(d_chal, d_chal_c, d_in + w_z1, d_in + w_z2, d_in + w_cip, d_in + w_ps, d_in + w_es, d_in + w_elm,
+                                                     d_rand, d_rand + n, n, (int)k, nc, npts, d_scalars);
+    c.launches += 6;
+    // points: sg, U, L_0, R_0, ..., C_0 .., delta, H  (canonical; U filled below)
+    uint8_t *h_pts = ib.h_pts.reserve(64 * (size_t)n * npp);
+    const uint8_t *h_can = c.curve[curve].host_canonical.data() + 64 * (size_t)c.curve[curve].depth;  // h
+    for (uint32_t t = 0; t < n; t++) {
+        const size_t i = idx[t];
+        uint8_t *o = h_pts + 64 * (size_t)t * npp;
+        std::memcpy(o, b.sg64 + 64 * i, 64);
+        std::memcpy(o + 64 * 2, b.lr64 + 64 * (i * 2 * k), 128 * (size_t)k);
+        std::memcpy(o + 64 * (2 + 2 * (size_t)k), b.commitments64 + 64 * (i * nc), 64 * (size_t)nc);
+        std::memcpy(o + 64 * (2 + 2 * (size_t)k + nc), b.delta64 + 64 * i, 64);
+        std::memcpy(o + 64 * (3 + 2 * (size_t)k + nc), h_can, 64);
+    }
+    CTX_CUDA_OK(cudaEventSynchronize(rs.fork));
+    {
+        host::GroupMap<F> gm;
+        parallel_for(n, [&](size_t t) {
+            E x;
+            E::from_bytes_le(h_t + 32 * t, x);
+            host::Affine<F> u = gm.to_group(x);
+            u.x.to_bytes_le(h_pts + 64 * (t * npp + 1));
+            u.y.to_bytes_le(h_pts + 64 * (t * npp + 1) + 32);
+        });
+    }
+    uint32_t *d_pts_can = ib.d_pts_can.reserve(16 * (size_t)n * npp);
+    affine *d_pts = ib.d_pts.reserve((size_t)n * npp);
+    xyzz *d_terms = ib.d_terms.reserve((size_t)n * npp);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_pts_can, h_pts, 64 * (size_t)n * npp, cudaMemcpyHostToDevice, rs.s));
+    launch_affine_to_mont(curve, d_pts_can, d_pts, n * npp, rs.s);
+    AccumulatorBatch ab;
+    ab.curve = curve;
+    ab.k = (int)k;
+    ab.m = n;
+    ab.ok.assign(n, 0);
+    RlcBatch rbt;
+    rlc_buffers(sb, ab, rbt);
+    k_ipa_point_terms<F><<<(n * npp + 63) / 64, 64, 0, rs.s>>>(d_pts, d_scalars, n * npp, d_terms);
+    k_ipa_sum_terms<F><<<n, 32, 0, rs.s>>>(d_terms, npp, rbt.d_scaled);
+    c.launches += 3;
+    fe *d_r = sb.d_r.reserve(2 * (size_t)n);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_r, d_rand + n, 32 * (size_t)n, cudaMemcpyDeviceToDevice, rs.s));
+    rlc_levels(c, rs, sb, ab, rbt, d_chal, d_r, nullptr);
+    for (uint32_t t = 0; t < n; t++) ok[idx[t]] = ab.ok[t];
 }
 
 static void run_accumulators(Context &c, AccRun &rs, AccumulatorBatch &ab, int mode) {
@@ -1328,6 +1486,35 @@ int mina_b200_state_accumulators_device(uint32_t m, const void *d_pre_wrap, cons
 
 int mina_b200_accumulator_check(const unsigned char *proof, size_t proof_len, uint8_t ok3[3]) {
     return mina_b200_accumulator_check_batch(1, &proof, &proof_len, MINA_B200_MODE_PER_PROOF, ok3);
+}
+
+int mina_b200_ipa_verify(int curve, const uint8_t *poseidon_table, const mina_b200_ipa_batch *batch, uint8_t *ok) {
+    try {
+        require_ready();
+        if (curve < 0 || curve > 1 || !batch || !ok) throw std::runtime_error("ipa_verify: bad arguments");
+        const mina_b200_ipa_batch &b = *batch;
+        if (b.n == 0) return 0;
+        Context &c = ctx();
+        if (b.rounds < (uint32_t)BPOLY_LO_BITS || b.rounds > 16 || (1u << b.rounds) > c.curve[curve].depth)
+            throw std::runtime_error("ipa_verify: rounds must be in [8, 16] and 2^rounds must not exceed the resident SRS");
+        if (b.n_points == 0 || b.n_points > 8 || b.n_comm > 4096) throw std::runtime_error("ipa_verify: bad shape");
+        if (b.sponge_mode > 1 || b.sponge_count > 2) throw std::runtime_error("ipa_verify: bad sponge mode");
+        if (curve == 0) {
+            poseidon::Params<FpParams> t;
+            if (!t.from_bytes(poseidon_table, (size_t)poseidon::TABLE_WORDS * 32)) throw std::runtime_error("ipa_verify: bad Poseidon table");
+            ipa_verify_t<FpParams, FqParams, true>(c, 0, t, b, ok);
+        } else {
+            poseidon::Params<FqParams> t;
+            if (!t.from_bytes(poseidon_table, (size_t)poseidon::TABLE_WORDS * 32)) throw std::runtime_error("ipa_verify: bad Poseidon table");
+            ipa_verify_t<FqParams, FpParams, false>(c, 1, t, b, ok);
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+    } catch (...) {
+        set_error("unknown error");
+    }
+    return -1;
 }
 
 // Merkle fold over caller-supplied leaves with a caller-supplied Poseidon table (parity hook for K3 and

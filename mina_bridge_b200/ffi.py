@@ -295,6 +295,48 @@ def merkle_fold(table: bytes, paths, leaves, roots):
     return [b for b in ok.raw], [int.from_bytes(folded.raw[32 * i : 32 * i + 32], "little") for i in range(n)]
 
 
+class IpaBatch(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_uint32), ("rounds", ctypes.c_uint32), ("n_comm", ctypes.c_uint32), ("n_points", ctypes.c_uint32),
+                ("sponge_mode", ctypes.c_uint32), ("sponge_count", ctypes.c_uint32),
+                ("sponge_state96", ctypes.c_char_p), ("cip32", ctypes.c_char_p), ("polyscale32", ctypes.c_char_p),
+                ("evalscale32", ctypes.c_char_p), ("z1_32", ctypes.c_char_p), ("z2_32", ctypes.c_char_p),
+                ("eval_points32", ctypes.c_char_p), ("delta64", ctypes.c_char_p), ("sg64", ctypes.c_char_p),
+                ("commitments64", ctypes.c_char_p), ("lr64", ctypes.c_char_p)]
+
+
+def ipa_verify(curve: int, table: bytes, openings, sponge_mode: int, sponge_count: int):
+    """Batched IPA final check (SRS::verify).  openings: list of dicts with ints / (x, y) points:
+    state[3], cip, polyscale, evalscale, z1, z2, elm[], delta, sg, commitments[], lr[(L, R)].  Returns [ok]."""
+    n = len(openings)
+    if n == 0:
+        return []
+    f32 = lambda x: int(x).to_bytes(32, "little")
+    pt = lambda p: (b"\0" * 64 if p is None else f32(p[0]) + f32(p[1]))
+    o0 = openings[0]
+    b = IpaBatch()
+    b.n, b.rounds, b.n_comm, b.n_points = n, len(o0["lr"]), len(o0["commitments"]), len(o0["elm"])
+    b.sponge_mode, b.sponge_count = sponge_mode, sponge_count
+    keep = []  # keep the byte strings alive for the duration of the call
+
+    def field(name, data):
+        keep.append(data)
+        setattr(b, name, data)
+
+    field("sponge_state96", b"".join(f32(x) for o in openings for x in o["state"]))
+    for name, key in (("cip32", "cip"), ("polyscale32", "polyscale"), ("evalscale32", "evalscale"), ("z1_32", "z1"), ("z2_32", "z2")):
+        field(name, b"".join(f32(o[key]) for o in openings))
+    field("eval_points32", b"".join(f32(x) for o in openings for x in o["elm"]))
+    field("delta64", b"".join(pt(o["delta"]) for o in openings))
+    field("sg64", b"".join(pt(o["sg"]) for o in openings))
+    field("commitments64", b"".join(pt(p) for o in openings for p in o["commitments"]))
+    field("lr64", b"".join(pt(l) + pt(r) for o in openings for (l, r) in o["lr"]))
+    ok = ctypes.create_string_buffer(n)
+    lib = load()
+    lib.mina_b200_ipa_verify.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p]
+    _check(lib.mina_b200_ipa_verify(curve, table, ctypes.byref(b), ok))
+    return [x for x in ok.raw]
+
+
 def poseidon_trusted() -> bool:
     return bool(load().mina_b200_poseidon_trusted())
 
