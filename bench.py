@@ -456,6 +456,68 @@ def bench_msm20(a, torch, dist, mb, rank, world, dev):
     }
 
 
+def bench_ipa(a, torch, dist, mb, rank, world, dev):
+    """Row a9 alone: BATCH openings of the wrap proof's shape (Pallas, 15 rounds, 47 commitments, 2 points; the committed
+    oracle-made fixture replicated, 1 % with a wrong z2) through mina_b200_ipa_verify.  The API takes host buffers, so the
+    number IS end to end; the Poseidon table is arbitrary (constants unavailable), which does not change the work."""
+    from mina_bridge_b200 import shard
+
+    curve, table, op, mode, count = mb.load_ipa_fixture(os.path.join(ROOT, "tests", "golden", "ipa_pallas_k15.json"))
+    bad = corrupt_positions()
+    Q = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
+    batch = [dict(op, z2=(op["z2"] + 1) % Q) if i in bad else op for i in range(BATCH)]
+    want = [0 if i in bad else 1 for i in range(BATCH)]
+    mine = shard.shard_indices(BATCH, rank, world)
+    my = [batch[i] for i in mine]
+    idx = torch.tensor(mine, dtype=torch.int64, device=dev)
+    result = torch.ones(BATCH, dtype=torch.uint8, device=dev)
+    pin = torch.empty(len(mine), dtype=torch.uint8).pin_memory()
+
+    packed = mb.ipa_pack(my, mode, count)  # the flat host buffers a caller hands to the C ABI
+
+    def step():
+        bits = mb.ipa_verify_packed(curve, table, packed)
+        pin.copy_(torch.frombuffer(bytearray(bits), dtype=torch.uint8))
+        return shard.merge_result_bytes(torch, dist, result, idx, pin.to(dev, non_blocking=True), world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    assert torch.equal(step(), torch.tensor(want, dtype=torch.uint8, device=dev)), "ipa: result bytes differ from the expected bits"
+    W = max(a.warmup, 3)
+    for _ in range(W):
+        step()
+    sampler = ClockSampler()
+    sampler.start()
+    l0 = mb.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    launches = mb.launch_count() - l0
+    sampler.stop.set()
+    sampler.join()
+    if rank != 0:
+        return None
+    v = BATCH * a.steps / float(t.item())
+    npp = 2 * 15 + 47 + 4
+    return {"metric": "ipa_final_checks_per_sec", "value": v, "unit": "openings/s", "n_gpus": world, "steps": a.steps, "warmup": W,
+            "ms_per_step": float(t.item()) / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u256 modular (8x32 Montgomery)", "data": "synthetic",
+            "config": {"workload": "ipa%d: SRS::verify of %d openings per step (Pallas, 15 rounds, 47 commitments, 2 points; oracle-made fixture x%d, %d with a wrong z2), "
+                                   "transcript + scalars + %d scalar multiplications per opening + batched g-side MSM" % (BATCH, BATCH, BATCH, len(bad), npp),
+                       "value_is_e2e": True, "poseidon_table": "arbitrary (kimchi constants unavailable): timing is independent of the constants, parity is unpinned"},
+            "roofline": None,
+            "e2e": {"value": v, "unit": "openings/s", "h2d_bytes_per_step": len(mine) * (96 + 32 * 7 + 64 * (2 + 30 + 47) + 64 * npp), "d2h_bytes_per_step": len(mine) * 33},
+            "gpu_launches": int(launches), "clocks": sampler.summary()}
+
+
 def main():
     global BATCH, N_CORRUPT
     ap = argparse.ArgumentParser()
@@ -463,7 +525,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20"])
+    ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20", "ipa"])
     ap.add_argument("--profile-step", default="", choices=["", "rlc", "per_proof"],
                     help="run one extra untimed step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off)")
     ap.add_argument("--batch", type=int, default=BATCH, help="proofs per step (default: the 1024 of BASELINE.json; 64 = configs[2])")
@@ -492,7 +554,7 @@ def main():
         dist.barrier()
     mb.init(local)
     dev = torch.device("cuda", local)
-    line = (bench_state if a.workload == "state1024" else bench_msm20)(a, torch, dist, mb, rank, world, dev)
+    line = {"state1024": bench_state, "msm20": bench_msm20, "ipa": bench_ipa}[a.workload](a, torch, dist, mb, rank, world, dev)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

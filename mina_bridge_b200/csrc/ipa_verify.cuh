@@ -157,6 +157,79 @@ __global__ void __launch_bounds__(128) k_ipa_transcript(const fe *__restrict__ s
     }
 }
 
+// ---- U = to_group(t): the Shallue-van de Woestijne map of groupmap `BWParameters` with u = 1 -----------
+// Square root exactly as ark-ff 0.3 returns it (Tonelli-Shanks with the 2^32-th root of unity 5^t): the SIGN of
+// y matters here because no file supplies it.  Same algorithm as host_field.hpp `Fe::sqrt`, which the derivation
+// of the committed SRS pins.
+template <class F>
+__device__ bool fe_sqrt(const fe &a, fe &out) {
+    if (fe_is_zero(a)) {
+        out = a;
+        return true;
+    }
+    const uint64_t half[4] = {F::HALF_64(0), F::HALF_64(1), F::HALF_64(2), F::HALF_64(3)};
+    const fe one = Fd<F>::one();
+    if (!fe_eq(Fd<F>::pow_u256(a, half), one)) return false;
+    const uint64_t tm[4] = {F::T_MINUS1_DIV2_64(0), F::T_MINUS1_DIV2_64(1), F::T_MINUS1_DIV2_64(2), F::T_MINUS1_DIV2_64(3)};
+    fe z;
+#pragma unroll
+    for (int i = 0; i < 8; i++) z.v[i] = F::ROOT_OF_UNITY(i);
+    fe w = Fd<F>::pow_u256(a, tm);
+    fe x = Fd<F>::mul(a, w);
+    fe b = Fd<F>::mul(x, w);
+    int v = 32;
+    while (!fe_eq(b, one)) {
+        int k = 0;
+        fe b2k = b;
+        while (!fe_eq(b2k, one)) {
+            b2k = Fd<F>::sqr(b2k);
+            k++;
+        }
+        w = z;
+        for (int i = 0; i < v - k - 1; i++) w = Fd<F>::sqr(w);
+        z = Fd<F>::sqr(w);
+        b = Fd<F>::mul(b, z);
+        x = Fd<F>::mul(x, w);
+        v = k;
+    }
+    out = x;
+    return true;
+}
+struct GroupMapConsts {  // Montgomery, computed once on the host (srs.hpp GroupMap)
+    fe sqrt_neg_three, sqrt_neg_three_minus_one_over_two, inv_three;
+};
+// out[i * stride + slot] = to_group(t[i]) as a Montgomery affine point
+template <class F>
+__global__ void __launch_bounds__(64) k_to_group(const fe *__restrict__ t_can, uint32_t n, GroupMapConsts gm, affine *__restrict__ out,
+                                                 uint32_t stride, uint32_t slot) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fe one = Fd<F>::one(), five = Fd<F>::five();
+    const fe fu = Fd<F>::add(one, five);  // u^3 + b with u = 1
+    fe t = Fd<F>::to_mont(t_can[i]);
+    fe t2 = Fd<F>::sqr(t);
+    fe t2_fu = Fd<F>::add(t2, fu);
+    fe alpha_inv = Fd<F>::mul(t2_fu, t2);
+    fe alpha = fe_is_zero(alpha_inv) ? alpha_inv : Fd<F>::inv(alpha_inv);
+    fe xs[3];
+    xs[0] = Fd<F>::sub(gm.sqrt_neg_three_minus_one_over_two, Fd<F>::mul(Fd<F>::mul(Fd<F>::sqr(t2), alpha), gm.sqrt_neg_three));
+    xs[1] = Fd<F>::sub(Fd<F>::neg(one), xs[0]);
+    xs[2] = Fd<F>::sub(one, Fd<F>::mul(Fd<F>::mul(Fd<F>::sqr(t2_fu), Fd<F>::mul(alpha, t2_fu)), gm.inv_three));
+    affine p;
+    p.x = fe_zero();
+    p.y = fe_zero();
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        fe y;
+        if (fe_sqrt<F>(Fd<F>::add(Fd<F>::mul(Fd<F>::sqr(xs[k]), xs[k]), five), y)) {
+            p.x = xs[k];
+            p.y = y;
+            break;
+        }
+    }
+    out[(size_t)i * stride + slot] = p;
+}
+
 // Scalars of the per-opening points, one thread per opening.  All inputs canonical except the challenges
 // (Montgomery: k round challenges per opening, and c) and the two randomisers (Montgomery).  Output: canonical scalars in the order
 //   sg, U, L_0, R_0, ..., L_{k-1}, R_{k-1}, C_0 .. C_{nc-1}, delta, H          (2k + nc + 4 per opening)

@@ -523,40 +523,62 @@ __global__ void __launch_bounds__(32) k_bit_sums(const xyzz *__restrict__ last, 
     if (lane == 0) out[(size_t)g * tp.slots + slot] = acc;
 }
 
-// One warp per MSM: Horner over the bit sums (lane k doubles U_k k times, then a shuffle tree), unwind the
-// running-sum passes, combine windows, normalise.
+// One warp per group (= one window of one MSM): Horner over the bit sums (lane k doubles U_k k times, then a shuffle
+// tree) and unwinding of the running-sum passes.  Valid in lane 0.
 //   pass l turned points B with weights (b+1) into S (weights t) and W:  sum = sum W + m_l * sum_t t*S_t
 //   below the last pass the weights are t, above it they are (t+1):  D_l = sumW_l + m_l * (D_{l+1} - T).
-// AFFINE = false leaves the result in XYZZ form (no field inversion): callers that only COMPARE results
-// (the accumulator checks) cross-multiply instead of normalising.
+template <class F>
+__device__ __forceinline__ xyzz group_result(const xyzz *__restrict__ base, const TailParams &tp, uint32_t lane) {
+    xyzz V = lane < (uint32_t)tp.nbits ? base[lane] : Ec<F>::identity();
+    for (uint32_t k = 0; k < lane && lane < (uint32_t)tp.nbits; k++) V = Ec<F>::dbl(V);
+    xyzz D = warp_sum_points<F>(V);  // Z = sum_t t * B_t
+    xyzz T = warp_sum_points<F>(lane < tp.parts_last ? base[tp.nbits + lane] : Ec<F>::identity());
+    if (tp.L == 0) {
+        Ec<F>::add(D, T);  // bucket b weighs b + 1
+    } else {
+        xyzz negT = T;
+        negT.y = Fd<F>::neg(negT.y);
+        for (int l = tp.L - 1; l >= 0; l--) {
+            if (l != tp.L - 1) Ec<F>::add(D, negT);
+            for (int k = 0; k < tp.log_m[l]; k++) D = Ec<F>::dbl(D);
+            xyzz Wl = warp_sum_points<F>(lane < tp.w_parts[l] ? base[tp.w_slot[l] + lane] : Ec<F>::identity());
+            Ec<F>::add(D, Wl);
+        }
+    }
+    return D;
+}
+// Fixed-base engine (one group per MSM): the group result IS the MSM.  AFFINE = false leaves the result in XYZZ
+// form (no field inversion): callers that only COMPARE results (the accumulator checks) cross-multiply instead.
 template <class F, bool AFFINE>
 __global__ void __launch_bounds__(32) k_finalize(const xyzz *__restrict__ sums /* [groups][slots] */, TailParams tp,
                                                  void *__restrict__ out_any) {
     const uint32_t msm = blockIdx.x, lane = threadIdx.x;
+    xyzz res = group_result<F>(sums + (size_t)msm * tp.slots, tp, lane);
+    if (lane != 0) return;
+    if (AFFINE)
+        reinterpret_cast<affine *>(out_any)[msm] = Ec<F>::to_affine(res);
+    else
+        reinterpret_cast<xyzz *>(out_any)[msm] = res;
+}
+// Generic bases: every window of every MSM gets its own warp (the tails of W windows in ONE warp cost W x 0.2 ms) ...
+template <class F>
+__global__ void __launch_bounds__(32) k_window_results(const xyzz *__restrict__ sums, TailParams tp, xyzz *__restrict__ out) {
+    xyzz D = group_result<F>(sums + (size_t)blockIdx.x * tp.slots, tp, threadIdx.x);
+    if (threadIdx.x == 0) out[blockIdx.x] = D;
+}
+// ... and one thread per MSM combines them: res = sum_w 2^(c w) D_w by Horner (255 doublings, the latency floor of any
+// variable-base MSM).
+template <class F, bool AFFINE>
+__global__ void __launch_bounds__(32) k_combine_windows(const xyzz *__restrict__ win /* [nmsm][W] */, TailParams tp,
+                                                        void *__restrict__ out_any, uint32_t nmsm) {
+    const uint32_t msm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (msm >= nmsm) return;
     xyzz res = Ec<F>::identity();
     for (int w = tp.W - 1; w >= 0; w--) {
-        const xyzz *base = sums + (size_t)(msm * tp.W + w) * tp.slots;
-        xyzz V = lane < (uint32_t)tp.nbits ? base[lane] : Ec<F>::identity();
-        for (uint32_t k = 0; k < lane && lane < (uint32_t)tp.nbits; k++) V = Ec<F>::dbl(V);
-        xyzz D = warp_sum_points<F>(V);  // Z = sum_t t * B_t
-        xyzz T = warp_sum_points<F>(lane < tp.parts_last ? base[tp.nbits + lane] : Ec<F>::identity());
-        if (tp.L == 0) {
-            Ec<F>::add(D, T);  // bucket b weighs b + 1
-        } else {
-            xyzz negT = T;
-            negT.y = Fd<F>::neg(negT.y);
-            for (int l = tp.L - 1; l >= 0; l--) {
-                if (l != tp.L - 1) Ec<F>::add(D, negT);
-                for (int k = 0; k < tp.log_m[l]; k++) D = Ec<F>::dbl(D);
-                xyzz Wl = warp_sum_points<F>(lane < tp.w_parts[l] ? base[tp.w_slot[l] + lane] : Ec<F>::identity());
-                Ec<F>::add(D, Wl);
-            }
-        }
         if (w != tp.W - 1)
             for (int k = 0; k < tp.c; k++) res = Ec<F>::dbl(res);
-        Ec<F>::add(res, D);
+        Ec<F>::add(res, win[(size_t)msm * tp.W + w]);
     }
-    if (lane != 0) return;
     if (AFFINE)
         reinterpret_cast<affine *>(out_any)[msm] = Ec<F>::to_affine(res);
     else
@@ -946,11 +968,21 @@ class MsmEngine : public MsmEngineBase {
             N /= m;
         }
         k_bit_sums<F><<<dim3(groups, tp.slots), 32, 0, s>>>(in, lvlW_, tp, sums_);
-        if (affine_out)
-            k_finalize<F, true><<<nmsm, 32, 0, s>>>(sums_, tp, d_out);
-        else
-            k_finalize<F, false><<<nmsm, 32, 0, s>>>(sums_, tp, d_out);
-        launches_ += 2;
+        if (tp.W == 1) {
+            if (affine_out)
+                k_finalize<F, true><<<nmsm, 32, 0, s>>>(sums_, tp, d_out);
+            else
+                k_finalize<F, false><<<nmsm, 32, 0, s>>>(sums_, tp, d_out);
+            launches_ += 2;
+        } else {
+            xyzz *win = lvlS_[0];  // free again: the bit sums have consumed the last pass (>= groups entries: nbw >= 2)
+            k_window_results<F><<<groups, 32, 0, s>>>(sums_, tp, win);
+            if (affine_out)
+                k_combine_windows<F, true><<<(nmsm + 31) / 32, 32, 0, s>>>(win, tp, d_out, nmsm);
+            else
+                k_combine_windows<F, false><<<(nmsm + 31) / 32, 32, 0, s>>>(win, tp, d_out, nmsm);
+            launches_ += 3;
+        }
         CUDA_OK(cudaGetLastError());
     }
 

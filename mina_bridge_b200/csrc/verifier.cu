@@ -49,7 +49,7 @@ struct SideBuffers {  // one accumulator family (Vesta k=16 or Pallas k=15)
     DevBuf<xyzz> d_xyzz, d_scaled;
 };
 struct IpaBuffers {  // the batched IPA final check (one per curve)
-    PinnedBuf<uint8_t> h_in, h_t, h_pts;
+    PinnedBuf<uint8_t> h_in, h_pts;
     DevBuf<uint8_t> d_in;
     DevBuf<fe> d_tab, d_t, d_chal, d_chal_c, d_rand, d_scalars;
     DevBuf<uint4> d_pre;
@@ -375,6 +375,11 @@ static __global__ void __launch_bounds__(SUBSET_THREADS) k_derive_last_child(con
     }
 }
 template <class F>
+static __global__ void k_negate_xyzz(xyzz *p, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i].y = Fd<F>::neg(p[i].y);
+}
+template <class F>
 static __device__ __forceinline__ bool xyzz_equal(const xyzz &p, const xyzz &q) {
     bool pi = fe_is_zero(p.zz), qi = fe_is_zero(q.zz);
     if (pi || qi) return pi && qi;
@@ -472,6 +477,10 @@ struct RlcBatch {
     xyzz *d_scaled = nullptr, *d_scaled_w = nullptr;  // P_j, (j + 1) P_j
     uint32_t n_slices0 = 0;
     bool weighted = false;  // the *_w members are built (only after level 0 failed)
+    // IPA: level 0 may take the commitment-side sum of the WHOLE batch from one Pippenger MSM over all per-opening
+    // points (d_D0) and produce the per-item P_j only if level 0 fails (materialize enqueues that work on rs.s)
+    const xyzz *d_D0 = nullptr;
+    std::function<void()> materialize;
 };
 
 // One level of checks, ALL groups in one launch set.  status[g] as in k_locate.
@@ -523,7 +532,9 @@ static std::vector<uint32_t> acc_check_groups(Context &c, AccRun &rs, SideBuffer
     // commitment side on the auxiliary stream, beside the MSM
     CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));
     CTX_CUDA_OK(cudaStreamWaitEvent(rs.aux, rs.fork, 0));
-    if (ab.curve == 0)
+    if (!locator && rb.d_D0)
+        CTX_CUDA_OK(cudaMemcpyAsync(d_D, rb.d_D0, sizeof(xyzz), cudaMemcpyDeviceToDevice, rs.aux));
+    else if (ab.curve == 0)
         k_range_sums<FpParams><<<dim3(G, nv), SUBSET_THREADS, 0, rs.aux>>>(rb.d_scaled, rb.d_scaled_w, d_meta + o_rng, d_D, stride);
     else
         k_range_sums<FqParams><<<dim3(G, nv), SUBSET_THREADS, 0, rs.aux>>>(rb.d_scaled, rb.d_scaled_w, d_meta + o_rng, d_D, stride);
@@ -698,6 +709,9 @@ static void rlc_levels(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch
                 return;
             }
             // something is bad: build the locator-weighted twins once, then test the whole batch again with both sums
+            if (rb.materialize) rb.materialize();  // per-item P_j that level 0 did without
+            CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));
+            CTX_CUDA_OK(cudaStreamWaitEvent(rs.aux, rs.fork, 0));
             if (ab.curve == 0) {
                 k_weight_points<FpParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(rb.d_scaled, ab.m, rb.d_scaled_w);
                 k_weight_scalars<FqParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_r, ab.m, d_r + ab.m);
@@ -774,11 +788,48 @@ template <class F, class S, bool SCALAR_LARGER>
 static void ipa_verify_t(Context &c, int curve, const poseidon::Params<F> &table, const mina_b200_ipa_batch &b, uint8_t *ok) {
     using E = host::Fe<F>;
     using ES = host::Fe<S>;
-    const uint32_t n_all = b.n, k = b.rounds, nc = b.n_comm, npts = b.n_points;
+    const uint32_t n = b.n, k = b.rounds, nc = b.n_comm, npts = b.n_points;
     const uint32_t npp = 2 * k + nc + 4;
-    std::memset(ok, 0, n_all);
-    // host validation: canonical field elements, points on the curve ((0,0) = identity allowed for commitments only)
-    std::vector<uint8_t> valid(n_all, 1);
+    std::memset(ok, 0, n);
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    AccRun rs;
+    setup_run(c, rs, 0, false);
+    IpaBuffers &ib = vstate().ipa[curve];
+    SideBuffers &sb = vstate().side[curve];
+    CurveCtx &cc = c.curve[curve];
+    const int sfield = curve == 1 ? 0 : 1;  // scalar field id
+    // (1) everything the transcript and the scalar kernel read goes up unvalidated, so the sponge (the longest
+    // dependent chain of the whole check) starts at once; validation runs on the host meanwhile and neutralises bad
+    // openings through their randomisers (zero) and points (identity) before anything is summed across openings.
+    // packed 32-byte words: state[3n] | cip[n] | lr[4kn] | delta[2n] | z1 | z2 | polyscale | evalscale | elm[npts n]
+    const size_t w_state = 0, w_cip = w_state + 3 * (size_t)n, w_lr = w_cip + n, w_delta = w_lr + 4 * (size_t)k * n, w_z1 = w_delta + 2 * (size_t)n,
+                 w_z2 = w_z1 + n, w_ps = w_z2 + n, w_es = w_ps + n, w_elm = w_es + n, w_end = w_elm + (size_t)npts * n;
+    uint8_t *h_in = ib.h_in.reserve(32 * w_end);
+    std::memcpy(h_in + 32 * w_state, b.sponge_state96, 96 * (size_t)n);
+    std::memcpy(h_in + 32 * w_cip, b.cip32, 32 * (size_t)n);
+    std::memcpy(h_in + 32 * w_lr, b.lr64, 128 * (size_t)k * n);
+    std::memcpy(h_in + 32 * w_delta, b.delta64, 64 * (size_t)n);
+    std::memcpy(h_in + 32 * w_z1, b.z1_32, 32 * (size_t)n);
+    std::memcpy(h_in + 32 * w_z2, b.z2_32, 32 * (size_t)n);
+    std::memcpy(h_in + 32 * w_ps, b.polyscale32, 32 * (size_t)n);
+    std::memcpy(h_in + 32 * w_es, b.evalscale32, 32 * (size_t)n);
+    std::memcpy(h_in + 32 * w_elm, b.eval_points32, 32 * (size_t)npts * n);
+    const fe *d_in = reinterpret_cast<const fe *>(ib.d_in.reserve(32 * w_end));
+    CTX_CUDA_OK(cudaMemcpyAsync(ib.d_in.p, h_in, 32 * w_end, cudaMemcpyHostToDevice, rs.s));
+    auto tab = table.device_table();
+    fe *d_tab = ib.d_tab.reserve(POSEIDON_TABLE_WORDS);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, rs.s));
+    fe *d_t = ib.d_t.reserve(n);
+    uint4 *d_pre = ib.d_pre.reserve((size_t)n * (k + 1));
+    k_ipa_transcript<F, S, SCALAR_LARGER><<<(4 * n + 127) / 128, 128, 0, rs.s>>>(d_in + w_state, b.sponge_mode, b.sponge_count, d_in + w_cip, d_in + w_lr,
+                                                                             d_in + w_delta, n, (int)k, d_tab, d_t, d_pre, d_pre + (size_t)n * k);
+    fe *d_chal = ib.d_chal.reserve((size_t)n * k), *d_chal_c = ib.d_chal_c.reserve(n);
+    launch_endo_to_field(sfield, d_pre, d_chal, n * k, rs.s);
+    launch_endo_to_field(sfield, d_pre + (size_t)n * k, d_chal_c, n, rs.s);
+    c.launches += 3;
+    // (2) host validation: canonical field elements, points on the curve ((0,0) = identity allowed for commitments only)
+    std::vector<uint8_t> valid(n, 1);
     auto point_ok = [](const uint8_t *p, bool allow_identity) {
         host::Affine<F> a;
         if (!E::from_bytes_le(p, a.x) || !E::from_bytes_le(p + 32, a.y)) return false;
@@ -786,7 +837,11 @@ static void ipa_verify_t(Context &c, int curve, const poseidon::Params<F> &table
         a.inf = false;
         return a.on_curve();
     };
-    parallel_for(n_all, [&](size_t i) {
+    // points: sg, U (written on the device), L_0, R_0, ..., C_0 .., delta, H; randomisers rb | sgrb
+    uint8_t *h_pts = ib.h_pts.reserve(64 * (size_t)n * npp + 64 * (size_t)n);
+    uint8_t *h_rand = h_pts + 64 * (size_t)n * npp;
+    const uint8_t *h_can = cc.host_canonical.data() + 64 * (size_t)cc.depth;  // h
+    parallel_for(n, [&](size_t i) {
         bool good = true;
         E tmp;
         ES ts;
@@ -797,89 +852,41 @@ static void ipa_verify_t(Context &c, int curve, const poseidon::Params<F> &table
         for (uint32_t j = 0; j < 2 * k && good; j++) good = point_ok(b.lr64 + 64 * (i * 2 * k + j), false);
         for (uint32_t m = 0; m < nc && good; m++) good = point_ok(b.commitments64 + 64 * (i * nc + m), true);
         valid[i] = good;
-    });
-    std::vector<uint32_t> idx;
-    for (uint32_t i = 0; i < n_all; i++)
-        if (valid[i]) idx.push_back(i);
-    const uint32_t n = (uint32_t)idx.size();
-    if (!n) return;
-
-    std::lock_guard<std::mutex> lk(c.mu);
-    CTX_CUDA_OK(cudaSetDevice(c.device));
-    AccRun rs;
-    setup_run(c, rs, 0, false);
-    IpaBuffers &ib = vstate().ipa[curve];
-    SideBuffers &sb = vstate().side[curve];
-    const int sfield = curve == 1 ? 0 : 1;  // scalar field id
-    // packed input, all 32-byte words: state[3n] | cip[n] | lr[4kn] | delta[2n] | z1 | z2 | polyscale | evalscale | elm[npts n] | rb | sgrb
-    const size_t w_state = 0, w_cip = w_state + 3 * (size_t)n, w_lr = w_cip + n, w_delta = w_lr + 4 * (size_t)k * n, w_z1 = w_delta + 2 * (size_t)n,
-                 w_z2 = w_z1 + n, w_ps = w_z2 + n, w_es = w_ps + n, w_elm = w_es + n, w_rb = w_elm + (size_t)npts * n, w_sg = w_rb + n,
-                 w_end = w_sg + n;
-    uint8_t *h_in = ib.h_in.reserve(32 * w_end);
-    for (uint32_t t = 0; t < n; t++) {
-        const size_t i = idx[t];
-        std::memcpy(h_in + 32 * (w_state + 3 * t), b.sponge_state96 + 96 * i, 96);
-        std::memcpy(h_in + 32 * (w_cip + t), b.cip32 + 32 * i, 32);
-        std::memcpy(h_in + 32 * (w_lr + 4 * (size_t)k * t), b.lr64 + 64 * (i * 2 * k), 128 * (size_t)k);
-        std::memcpy(h_in + 32 * (w_delta + 2 * t), b.delta64 + 64 * i, 64);
-        std::memcpy(h_in + 32 * (w_z1 + t), b.z1_32 + 32 * i, 32);
-        std::memcpy(h_in + 32 * (w_z2 + t), b.z2_32 + 32 * i, 32);
-        std::memcpy(h_in + 32 * (w_ps + t), b.polyscale32 + 32 * i, 32);
-        std::memcpy(h_in + 32 * (w_es + t), b.evalscale32 + 32 * i, 32);
-        std::memcpy(h_in + 32 * (w_elm + (size_t)npts * t), b.eval_points32 + 32 * (i * npts), 32 * (size_t)npts);
-        random_128(h_in + 32 * (w_rb + t));
-        random_128(h_in + 32 * (w_sg + t));
-    }
-    const fe *d_in = reinterpret_cast<const fe *>(ib.d_in.reserve(32 * w_end));
-    CTX_CUDA_OK(cudaMemcpyAsync(ib.d_in.p, h_in, 32 * w_end, cudaMemcpyHostToDevice, rs.s));
-    auto tab = table.device_table();
-    fe *d_tab = ib.d_tab.reserve(POSEIDON_TABLE_WORDS);
-    CTX_CUDA_OK(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, rs.s));
-    fe *d_t = ib.d_t.reserve(n);
-    uint4 *d_pre = ib.d_pre.reserve((size_t)n * (k + 1));
-    k_ipa_transcript<F, S, SCALAR_LARGER><<<(4 * n + 127) / 128, 128, 0, rs.s>>>(d_in + w_state, b.sponge_mode, b.sponge_count, d_in + w_cip, d_in + w_lr,
-                                                                             d_in + w_delta, n, (int)k, d_tab, d_t, d_pre, d_pre + (size_t)n * k);
-    uint8_t *h_t = ib.h_t.reserve(32 * (size_t)n);
-    CTX_CUDA_OK(cudaMemcpyAsync(h_t, d_t, 32 * (size_t)n, cudaMemcpyDeviceToHost, rs.s));
-    CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));  // t is on the host once this event has fired
-    // everything that does not need U runs while the host maps t to the curve
-    fe *d_chal = ib.d_chal.reserve((size_t)n * k), *d_chal_c = ib.d_chal_c.reserve(n);
-    launch_endo_to_field(sfield, d_pre, d_chal, n * k, rs.s);
-    launch_endo_to_field(sfield, d_pre + (size_t)n * k, d_chal_c, n, rs.s);
-    fe *d_rand = ib.d_rand.reserve(2 * (size_t)n);  // rb | sgrb, Montgomery
-    launch_fe_to_mont(sfield, d_in + w_rb, d_rand, 2 * n, rs.s);
-    fe *d_scalars = ib.d_scalars.reserve((size_t)n * npp);
-    k_ipa_scalars<S><<<(n + 63) / 64, 64, 0, rs.s>>>(d_chal, d_chal_c, d_in + w_z1, d_in + w_z2, d_in + w_cip, d_in + w_ps, d_in + w_es, d_in + w_elm,
-                                                     d_rand, d_rand + n, n, (int)k, nc, npts, d_scalars);
-    c.launches += 6;
-    // points: sg, U, L_0, R_0, ..., C_0 .., delta, H  (canonical; U filled below)
-    uint8_t *h_pts = ib.h_pts.reserve(64 * (size_t)n * npp);
-    const uint8_t *h_can = c.curve[curve].host_canonical.data() + 64 * (size_t)c.curve[curve].depth;  // h
-    for (uint32_t t = 0; t < n; t++) {
-        const size_t i = idx[t];
-        uint8_t *o = h_pts + 64 * (size_t)t * npp;
+        uint8_t *o = h_pts + 64 * i * npp;
+        std::memset(h_rand + 32 * i, 0, 32);
+        std::memset(h_rand + 32 * (n + i), 0, 32);
+        if (!good) {
+            std::memset(o, 0, 64 * (size_t)npp);
+            return;
+        }
         std::memcpy(o, b.sg64 + 64 * i, 64);
+        std::memset(o + 64, 0, 64);
         std::memcpy(o + 64 * 2, b.lr64 + 64 * (i * 2 * k), 128 * (size_t)k);
         std::memcpy(o + 64 * (2 + 2 * (size_t)k), b.commitments64 + 64 * (i * nc), 64 * (size_t)nc);
         std::memcpy(o + 64 * (2 + 2 * (size_t)k + nc), b.delta64 + 64 * i, 64);
         std::memcpy(o + 64 * (3 + 2 * (size_t)k + nc), h_can, 64);
-    }
-    CTX_CUDA_OK(cudaEventSynchronize(rs.fork));
-    {
-        host::GroupMap<F> gm;
-        parallel_for(n, [&](size_t t) {
-            E x;
-            E::from_bytes_le(h_t + 32 * t, x);
-            host::Affine<F> u = gm.to_group(x);
-            u.x.to_bytes_le(h_pts + 64 * (t * npp + 1));
-            u.y.to_bytes_le(h_pts + 64 * (t * npp + 1) + 32);
-        });
-    }
-    uint32_t *d_pts_can = ib.d_pts_can.reserve(16 * (size_t)n * npp);
+        random_128(h_rand + 32 * i);
+        random_128(h_rand + 32 * (n + i));
+    });
+    uint32_t *d_pts_can = ib.d_pts_can.reserve(16 * (size_t)n * npp + 16 * (size_t)n);
     affine *d_pts = ib.d_pts.reserve((size_t)n * npp);
     xyzz *d_terms = ib.d_terms.reserve((size_t)n * npp);
-    CTX_CUDA_OK(cudaMemcpyAsync(d_pts_can, h_pts, 64 * (size_t)n * npp, cudaMemcpyHostToDevice, rs.s));
+    CTX_CUDA_OK(cudaMemcpyAsync(d_pts_can, h_pts, 64 * (size_t)n * npp + 64 * (size_t)n, cudaMemcpyHostToDevice, rs.s));
     launch_affine_to_mont(curve, d_pts_can, d_pts, n * npp, rs.s);
+    {
+        host::GroupMap<F> hm;
+        GroupMapConsts gm;
+        std::memcpy(&gm.sqrt_neg_three, hm.sqrt_neg_three_u2.l, 32);
+        std::memcpy(&gm.sqrt_neg_three_minus_one_over_two, hm.sqrt_neg_three_u2_minus_u_over_2.l, 32);
+        std::memcpy(&gm.inv_three, hm.inv_three_u2.l, 32);
+        k_to_group<F><<<(n + 63) / 64, 64, 0, rs.s>>>(d_t, n, gm, d_pts, npp, 1);
+    }
+    fe *d_rand = ib.d_rand.reserve(2 * (size_t)n);  // rb | sgrb, Montgomery (zero for an invalid opening)
+    launch_fe_to_mont(sfield, reinterpret_cast<const fe *>(d_pts_can + 16 * (size_t)n * npp), d_rand, 2 * n, rs.s);
+    fe *d_scalars = ib.d_scalars.reserve((size_t)n * npp);
+    k_ipa_scalars<S><<<(n + 63) / 64, 64, 0, rs.s>>>(d_chal, d_chal_c, d_in + w_z1, d_in + w_z2, d_in + w_cip, d_in + w_ps, d_in + w_es, d_in + w_elm,
+                                                     d_rand, d_rand + n, n, (int)k, nc, npts, d_scalars);
+    c.launches += 4;
     AccumulatorBatch ab;
     ab.curve = curve;
     ab.k = (int)k;
@@ -887,13 +894,34 @@ static void ipa_verify_t(Context &c, int curve, const poseidon::Params<F> &table
     ab.ok.assign(n, 0);
     RlcBatch rbt;
     rlc_buffers(sb, ab, rbt);
-    k_ipa_point_terms<F><<<(n * npp + 63) / 64, 64, 0, rs.s>>>(d_pts, d_scalars, n * npp, d_terms);
-    k_ipa_sum_terms<F><<<n, 32, 0, rs.s>>>(d_terms, npp, rbt.d_scaled);
-    c.launches += 3;
+    // (3) Level 0 needs only sum_i B_i: ONE Pippenger MSM over all n * npp points (a few 10^5 additions).  The
+    // per-opening B_i (npp full-width scalar multiplications each, ~30x the work) are produced only if level 0 fails.
+    // Window width: the signed-digit recoding leaves only 254 - c (W - 1) bits (+ a carry) for the top window, so for
+    // most c nearly every scalar hits a handful of top-window buckets; c = 16 (14 bits left, no carry window) and
+    // c = 8 (6 bits) are the widths where the top window stays spread out.
+    MsmConfig vcfg;
+    vcfg.precompute = false;
+    vcfg.c = n * npp >= (1u << 14) ? 16 : 8;
+    // on the auxiliary stream, beside the tables / combine / MSM of the g side
+    CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));
+    CTX_CUDA_OK(cudaStreamWaitEvent(rs.aux, rs.fork, 0));
+    cc.var->set_bases(d_pts, n * npp, vcfg, rs.aux);
+    xyzz *d_total = d_terms;  // slot 0 of the term scratch; the terms themselves only exist after a failed level 0
+    cc.var->run_xyzz(reinterpret_cast<const uint32_t *>(d_scalars), 1, n * npp, d_total, rs.aux);
+    k_negate_xyzz<F><<<1, 32, 0, rs.aux>>>(d_total, 1);
+    c.launches += 2;
+    rbt.d_D0 = d_total;
+    xyzz *d_scaled = rbt.d_scaled;
+    rbt.materialize = [&c, &rs, d_pts, d_scalars, d_terms, d_scaled, n, npp]() {
+        k_ipa_point_terms<F><<<(n * npp + 63) / 64, 64, 0, rs.s>>>(d_pts, d_scalars, n * npp, d_terms);
+        k_ipa_sum_terms<F><<<n, 32, 0, rs.s>>>(d_terms, npp, d_scaled);
+        c.launches += 2;
+    };
     fe *d_r = sb.d_r.reserve(2 * (size_t)n);
     CTX_CUDA_OK(cudaMemcpyAsync(d_r, d_rand + n, 32 * (size_t)n, cudaMemcpyDeviceToDevice, rs.s));
     rlc_levels(c, rs, sb, ab, rbt, d_chal, d_r, nullptr);
-    for (uint32_t t = 0; t < n; t++) ok[idx[t]] = ab.ok[t];
+    if (cc.var->take_error(rs.aux)) throw std::runtime_error("ipa_verify: scalar overflow flagged by the MSM engine");
+    for (uint32_t i = 0; i < n; i++) ok[i] = valid[i] ? ab.ok[i] : 0;
 }
 
 static void run_accumulators(Context &c, AccRun &rs, AccumulatorBatch &ab, int mode) {

@@ -304,19 +304,17 @@ class IpaBatch(ctypes.Structure):
                 ("commitments64", ctypes.c_char_p), ("lr64", ctypes.c_char_p)]
 
 
-def ipa_verify(curve: int, table: bytes, openings, sponge_mode: int, sponge_count: int):
-    """Batched IPA final check (SRS::verify).  openings: list of dicts with ints / (x, y) points:
-    state[3], cip, polyscale, evalscale, z1, z2, elm[], delta, sg, commitments[], lr[(L, R)].  Returns [ok]."""
+def ipa_pack(openings, sponge_mode: int, sponge_count: int):
+    """Pack a list of opening dicts (ints / (x, y) points: state[3], cip, polyscale, evalscale, z1, z2, elm[], delta, sg,
+    commitments[], lr[(L, R)]) into the flat host buffers of mina_b200_ipa_batch.  Returns (struct, keep-alive list)."""
     n = len(openings)
-    if n == 0:
-        return []
     f32 = lambda x: int(x).to_bytes(32, "little")
     pt = lambda p: (b"\0" * 64 if p is None else f32(p[0]) + f32(p[1]))
     o0 = openings[0]
     b = IpaBatch()
     b.n, b.rounds, b.n_comm, b.n_points = n, len(o0["lr"]), len(o0["commitments"]), len(o0["elm"])
     b.sponge_mode, b.sponge_count = sponge_mode, sponge_count
-    keep = []  # keep the byte strings alive for the duration of the call
+    keep = []  # keep the byte strings alive as long as the struct
 
     def field(name, data):
         keep.append(data)
@@ -330,11 +328,37 @@ def ipa_verify(curve: int, table: bytes, openings, sponge_mode: int, sponge_coun
     field("sg64", b"".join(pt(o["sg"]) for o in openings))
     field("commitments64", b"".join(pt(p) for o in openings for p in o["commitments"]))
     field("lr64", b"".join(pt(l) + pt(r) for o in openings for (l, r) in o["lr"]))
-    ok = ctypes.create_string_buffer(n)
+    return b, keep
+
+
+def ipa_verify_packed(curve: int, table: bytes, packed):
+    b = packed[0]
+    ok = ctypes.create_string_buffer(b.n)
     lib = load()
     lib.mina_b200_ipa_verify.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p]
     _check(lib.mina_b200_ipa_verify(curve, table, ctypes.byref(b), ok))
-    return [x for x in ok.raw]
+    return ok.raw
+
+
+def ipa_verify(curve: int, table: bytes, openings, sponge_mode: int, sponge_count: int):
+    """Batched IPA final check (SRS::verify).  Returns [ok] per opening."""
+    if not openings:
+        return []
+    return [x for x in ipa_verify_packed(curve, table, ipa_pack(openings, sponge_mode, sponge_count))]
+
+
+def load_ipa_fixture(path: str):
+    """tests/golden/ipa_*.json (tools/make_ipa_fixture.py) -> (curve, table bytes, opening dict, sponge mode, count)"""
+    import json
+
+    d = json.load(open(path))
+    num = lambda h: int(h, 16)
+    pt = lambda p: (num(p[0]), num(p[1]))
+    opening = {"state": [num(x) for x in d["state"]], "cip": num(d["cip"]), "polyscale": num(d["polyscale"]), "evalscale": num(d["evalscale"]),
+               "z1": num(d["z1"]), "z2": num(d["z2"]), "elm": [num(x) for x in d["elm"]], "delta": pt(d["delta"]), "sg": pt(d["sg"]),
+               "commitments": [pt(p) for p in d["commitments"]], "lr": [(pt(l), pt(r)) for l, r in d["lr"]]}
+    table = b"".join(num(x).to_bytes(32, "little") for x in d["table"])
+    return d["curve"], table, opening, d["sponge_mode"], d["sponge_count"]
 
 
 def poseidon_trusted() -> bool:

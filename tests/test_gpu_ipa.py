@@ -82,3 +82,21 @@ def test_ipa_openings_accept_and_mutations_reject(gpu, curve, k):
     assert gpu.ipa_verify(curve, tb, [m, good[1], m2], mode, count) == [0, 1, 0]
     # a different (wrong) Poseidon table changes every challenge: nothing verifies
     assert gpu.ipa_verify(curve, oposeidon.table_bytes(oposeidon.random_table(cv.base, 5)), good[:2], mode, count) == [0, 0]
+
+
+def test_ipa_kimchi_shape_fixture(gpu):
+    """One opening of the wrap proof's shape (Pallas, 15 rounds over the full 2^15 SRS, 47 commitments, 2 points) made
+    by the oracle prover (tools/make_ipa_fixture.py): accepted alone and in a batch; corrupted copies are singled out."""
+    import os
+    from conftest import GOLDEN
+
+    curve, table, op, mode, count = gpu.load_ipa_fixture(os.path.join(GOLDEN, "ipa_pallas_k15.json"))
+    assert (curve, len(op["lr"]), len(op["commitments"])) == (0, 15, 47)
+    assert gpu.ipa_verify(curve, table, [op], mode, count) == [1]
+    bad1 = dict(op, z2=(op["z2"] + 1) % pasta.Q)
+    bad2 = dict(op, lr=[(r, l) if j == 14 else (l, r) for j, (l, r) in enumerate(op["lr"])])  # L and R swapped in the last round
+    batch = [op] * 70
+    batch[3], batch[64], batch[69] = bad1, bad2, bad1
+    want = [1] * 70
+    want[3] = want[64] = want[69] = 0
+    assert gpu.ipa_verify(curve, table, batch, mode, count) == want
