@@ -100,3 +100,32 @@ def test_ipa_kimchi_shape_fixture(gpu):
     want = [1] * 70
     want[3] = want[64] = want[69] = 0
     assert gpu.ipa_verify(curve, table, batch, mode, count) == want
+
+
+@pytest.mark.parametrize("prefix", ["a", "aa", "aaa", "as", "ass", "asa"])
+def test_ipa_resumes_the_sponge_in_every_mode(gpu, prefix):
+    """The Fq-sponge is handed over mid-stream: Absorbed(1), Absorbed(2), Absorbed(1) after a permutation, Squeezed(1),
+    Squeezed(2), and absorbing again after a squeeze.  The device transcript must resume each of them like the oracle."""
+    curve, k = 0, 8
+    cv = ipa.CurveCtx(curve)
+    table = oposeidon.random_table(cv.base, 4242)
+    g = gpu.srs_points(curve, 0, 1 << k)
+    h_pt = cref.bytes_to_point(gpu.srs_points(curve, 0, 1, want_h=True)[1])
+    rng = random.Random(len(prefix) * 7 + sum(map(ord, prefix)))
+    items = []
+    for _ in range(2):
+        polys = [[rng.randrange(cv.scalar) for _ in range(1 << k)] for _ in range(2)]
+        comms = [ipa.commit(cv, g, f) for f in polys]
+        elm = [rng.randrange(cv.scalar) for _ in range(2)]
+        polyscale, evalscale = rng.randrange(cv.scalar), rng.randrange(cv.scalar)
+        sp = ipa.FqSponge(cv, table)
+        for ch in prefix:
+            sp.absorb_fq(rng.randrange(cv.base)) if ch == "a" else sp.challenge_fq()
+        state, mode, count = sp.export()
+        opening, cip = ipa.open_proof(cv, g, h_pt, k, polys, elm, polyscale, evalscale, copy.deepcopy(sp), rng)
+        items.append({"state": state, "cip": cip, "polyscale": polyscale, "evalscale": evalscale, "z1": opening["z1"], "z2": opening["z2"],
+                      "elm": elm, "delta": opening["delta"], "sg": opening["sg"], "commitments": comms, "lr": opening["lr"]})
+    tb = oposeidon.table_bytes(table)
+    assert gpu.ipa_verify(curve, tb, items, mode, count) == [1, 1], (mode, count)
+    bad = dict(items[1], cip=(items[1]["cip"] + 1) % cv.scalar)
+    assert gpu.ipa_verify(curve, tb, [items[0], bad], mode, count) == [1, 0]
