@@ -503,6 +503,12 @@ def bench_ipa(a, torch, dist, mb, rank, world, dev):
     launches = mb.launch_count() - l0
     sampler.stop.set()
     sampler.join()
+    if a.profile_step:  # one extra untimed step inside a cudaProfilerStart/Stop range (ncu --profile-from-start off)
+        barrier()
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if rank != 0:
         return None
     v = BATCH * a.steps / float(t.item())
@@ -518,6 +524,86 @@ def bench_ipa(a, torch, dist, mb, rank, world, dev):
             "gpu_launches": int(launches), "clocks": sampler.summary()}
 
 
+def bench_mixed(a, torch, dist, mb, rank, world, dev):
+    """BASELINE configs[4]: BATCH/2 proof-of-state + BATCH/2 proof-of-account inputs per step through the two batch entry
+    points (host buffers in, result bytes out, one all-reduce(MIN)).  Built stages only: see config.absent_stages."""
+    from mina_bridge_b200 import shard
+
+    half = BATCH // 2
+    s_proofs, s_pubs, s_want = synth_batch()
+    s_proofs, s_pubs, s_want = s_proofs[:half], s_pubs[:half], s_want[:half]
+    ap, aq = golden("mina_account.proof"), golden("mina_account.pub")
+    bad = {i for i in corrupt_positions() if i >= half}
+    a_proofs, a_want = [], []
+    for i in range(half, 2 * half):
+        if i in bad:  # one flipped balance byte: the ABI comparison must fail
+            m = bytearray(ap)
+            m[1548 + 89] ^= 1
+            a_proofs.append(bytes(m))
+            a_want.append(0)
+        else:
+            a_proofs.append(ap)
+            a_want.append(1)
+    want = s_want + a_want
+    mine = shard.shard_indices(2 * half, rank, world)
+    my_s = [i for i in mine if i < half]
+    my_a = [i - half for i in mine if i >= half]
+    hs, hq = mb.Batch([s_proofs[i] for i in my_s]), mb.Batch([s_pubs[i] for i in my_s])
+    ha, haq = mb.Batch([a_proofs[i] for i in my_a]), mb.Batch([aq] * len(my_a))
+    S = mb.STAGES
+    built_s = 0
+    for k in ("lengths", "decode_proof", "decode_pub", "pub_structure", "consensus", "accumulator", "step_accumulators"):
+        built_s |= S[k]
+    built_a = S["lengths"] | S["decode_proof"] | S["decode_pub"] | S["account_abi"]
+    idx = torch.tensor(mine, dtype=torch.int64, device=dev)
+    result = torch.ones(2 * half, dtype=torch.uint8, device=dev)
+    pin = torch.empty(len(mine), dtype=torch.uint8).pin_memory()
+
+    def step():
+        _, rs = mb.verify_state_stages(hs, hq, mb.MODE_RLC)
+        _, ra = mb.verify_account_stages(ha, haq)
+        bits = [int(r.failed == 0 and (r.passed & built_s) == built_s) for r in rs] + [int(r.failed == 0 and (r.passed & built_a) == built_a) for r in ra]
+        order = {g: j for j, g in enumerate(my_s + [half + x for x in my_a])}
+        pin.copy_(torch.tensor([bits[order[g]] for g in mine], dtype=torch.uint8))
+        return shard.merge_result_bytes(torch, dist, result, idx, pin.to(dev, non_blocking=True), world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    assert torch.equal(step(), torch.tensor(want, dtype=torch.uint8, device=dev)), "mixed: result bytes differ from the expected bits"
+    W = max(a.warmup, 3)
+    for _ in range(W):
+        step()
+    sampler = ClockSampler()
+    sampler.start()
+    l0 = mb.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    launches = mb.launch_count() - l0
+    sampler.stop.set()
+    sampler.join()
+    if rank != 0:
+        return None
+    v = 2 * half * a.steps / float(t.item())
+    return {"metric": "mina_mixed_proofs_per_sec_built_stages", "value": v, "unit": "proofs/s", "n_gpus": world, "steps": a.steps, "warmup": W,
+            "ms_per_step": float(t.item()) / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u256 modular (8x32 Montgomery)", "data": "synthetic",
+            "config": {"workload": "mixed%d: %d proof-of-state + %d proof-of-account inputs per step (reference fixtures replicated, 1 %% corrupted), host buffers through the two batch entry points" % (2 * half, half, half),
+                       "value_is_e2e": True, "built_stages": BUILT + ["account: bincode decode", "account: Solidity ABI re-encoding == public input"],
+                       "absent_stages": ABSENT + ["account: Account::hash", "account: Merkle fold (kernel exists; needs the leaf hash and a trusted Poseidon table)"]},
+            "roofline": None,
+            "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": len(my_s) * (256 + 64 + 480 + 128 + 3 * 32), "d2h_bytes_per_step": 2 * 128 + 2 * half},
+            "gpu_launches": int(launches), "clocks": sampler.summary()}
+
+
 def main():
     global BATCH, N_CORRUPT
     ap = argparse.ArgumentParser()
@@ -525,7 +611,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20", "ipa"])
+    ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20", "ipa", "mixed"])
     ap.add_argument("--profile-step", default="", choices=["", "rlc", "per_proof"],
                     help="run one extra untimed step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off)")
     ap.add_argument("--batch", type=int, default=BATCH, help="proofs per step (default: the 1024 of BASELINE.json; 64 = configs[2])")
@@ -554,7 +640,7 @@ def main():
         dist.barrier()
     mb.init(local)
     dev = torch.device("cuda", local)
-    line = {"state1024": bench_state, "msm20": bench_msm20, "ipa": bench_ipa}[a.workload](a, torch, dist, mb, rank, world, dev)
+    line = {"state1024": bench_state, "msm20": bench_msm20, "ipa": bench_ipa, "mixed": bench_mixed}[a.workload](a, torch, dist, mb, rank, world, dev)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -375,6 +375,42 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const uint32_t *__restric
 template <class F>
 __device__ __forceinline__ xyzz shfl_down_point(const xyzz &p, int delta);
 
+// Few buckets (a single MSM, the first levels of the group testing): one thread per bucket leaves most of the GPU idle
+// and the launch lasts as long as the fullest bucket's ~50 dependent additions.  Here TPB adjacent lanes share a bucket:
+// each walks a contiguous part of its point list, then the parts are added with a shuffle tree (log2 TPB additions).
+template <class F, int TPB>
+__global__ void __launch_bounds__(128) k_accumulate_split(const uint32_t *__restrict__ order, const uint32_t *__restrict__ offsets,
+                                                          const uint32_t *__restrict__ pairs, const affine *__restrict__ table,
+                                                          xyzz *__restrict__ buckets, uint32_t nbuckets) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t slot = t / TPB, part = t % TPB;
+    const bool live = slot < nbuckets;  // whole warps stay for the shuffles (nbuckets * TPB need not fill the last warp)
+    uint32_t b = 0, k = 0, end = 0;
+    if (live) {
+        b = order[slot];
+        k = offsets[b];
+        end = offsets[b + 1];
+        if (end - k > ACC_SEG) end = k + ACC_SEG;
+        const uint32_t cnt = end - k, per = (cnt + TPB - 1) / TPB;
+        const uint32_t lo = k + part * per;
+        end = lo + per < end ? lo + per : end;
+        k = lo < end ? lo : end;
+    }
+    xyzz acc = Ec<F>::identity();
+    for (; k < end; k++) {
+        uint32_t e = pairs[k];
+        affine q = load_point<F>(table, e);
+        if (e >> 31) q.y = Fd<F>::neg(q.y);
+        add_mixed_compact<F>(acc, q);
+    }
+#pragma unroll 1
+    for (int d = TPB / 2; d >= 1; d >>= 1) {
+        xyzz o = shfl_down_point<F>(acc, d);
+        if (part + d < TPB) Ec<F>::add(acc, o);
+    }
+    if (live && part == 0) buckets[b] = acc;
+}
+
 // Over-full buckets: one block per listed bucket (block-stride), threads stride over the points past
 // ACC_SEG, then a shuffle / shared-memory tree; the block's sum is added into the bucket.
 static constexpr int OVER_THREADS = 256;
@@ -942,7 +978,13 @@ class MsmEngine : public MsmEngineBase {
             }
             CUDA_OK(cudaEventRecord(ev_[2 * ev_used_], s));
         }
-        k_accumulate<F><<<(nb + 127) / 128, 128, 0, s>>>(order_, offsets_, pairs_, table_, buckets_, nb);
+        // enough buckets to fill the GPU (148 SMs x 4 blocks x 128 threads): one thread per bucket; fewer: share buckets
+        if (nb > 4u * 32768u)
+            k_accumulate<F><<<(nb + 127) / 128, 128, 0, s>>>(order_, offsets_, pairs_, table_, buckets_, nb);
+        else if (nb > 32768u)
+            k_accumulate_split<F, 2><<<(2 * nb + 127) / 128, 128, 0, s>>>(order_, offsets_, pairs_, table_, buckets_, nb);
+        else
+            k_accumulate_split<F, 4><<<(4 * nb + 127) / 128, 128, 0, s>>>(order_, offsets_, pairs_, table_, buckets_, nb);
         launches_++;
         if (timing_) {
             CUDA_OK(cudaEventRecord(ev_[2 * ev_used_ + 1], s));

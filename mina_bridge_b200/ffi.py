@@ -220,7 +220,7 @@ def verify_state_batch(proofs, pubs):
 
 
 def verify_account_stages(proofs, pubs):
-    p, q = Batch(proofs), Batch(pubs)
+    p, q = (proofs if isinstance(proofs, Batch) else Batch(proofs)), (pubs if isinstance(pubs, Batch) else Batch(pubs))
     reports = (StageReport * max(p.n, 1))()
     accept = (ctypes.c_uint8 * max(p.n, 1))()
     lib = load()
