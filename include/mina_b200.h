@@ -80,6 +80,10 @@ int mina_b200_fixed_base_load(int curve, uint32_t n, const uint8_t *points64, in
 int mina_b200_fixed_base_msm(int curve, uint32_t nmsm, const uint8_t *scalars32, uint8_t *out64);
 int mina_b200_fixed_base_msm_device(int curve, uint32_t nmsm, const void *d_scalars, void *d_out64, void *cuda_stream,
                                     float *accumulate_ms);
+/* Commitments of the Lagrange polynomials L_first .. L_{first+count-1} of the radix-2 domain of size 2^log_n over the
+ * resident SRS (kimchi `SRS::add_lagrange_basis`, AL/operator/mina/lib/src/verifier_index.rs:204-208; the verifier's
+ * public-input commitment is -sum_i pub_i L_i + h over the first `public` = 40 of them).  2^log_n <= SRS depth. */
+int mina_b200_lagrange_commitments(int curve, uint32_t log_n, uint32_t first, uint32_t count, uint8_t *out64);
 /* MSM engine tuning (takes effect at the next init / table rebuild): window bits and running-sum
  * chunk.  Returns 0 on success. */
 int mina_b200_msm_configure(int curve, int window_bits, int precompute, int leaf);

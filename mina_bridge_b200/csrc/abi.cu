@@ -173,6 +173,16 @@ using namespace pasta;
         return -1;                         \
     }
 
+template <class S>
+static void lagrange_consts(uint32_t log_n, fe &omega_inv, fe &n_inv) {
+    using E = host::Fe<S>;
+    E w{{S::ROOT_OF_UNITY_64(0), S::ROOT_OF_UNITY_64(1), S::ROOT_OF_UNITY_64(2), S::ROOT_OF_UNITY_64(3)}};  // order 2^32
+    for (uint32_t i = log_n; i < 32; i++) w = w.sqr();  // order 2^log_n: the domain generator (K-G for log_n = 14 over Fq)
+    E wi = w.inv(), ni = E::from_u64(1ull << log_n).inv();
+    std::memcpy(&omega_inv, wi.l, 32);
+    std::memcpy(&n_inv, ni.l, 32);
+}
+
 extern "C" {
 
 const char *mina_b200_last_error(void) { return g_last_error.c_str(); }
@@ -293,6 +303,45 @@ int mina_b200_msm_srs_device(int curve, uint32_t nmsm, uint32_t n, const void *d
         CTX_CUDA_OK(cudaStreamSynchronize(s));
         *accumulate_ms = cc.fixed->last_accumulate_ms();
     }
+    return 0;
+    ABI_CATCH
+}
+
+int mina_b200_lagrange_commitments(int curve, uint32_t log_n, uint32_t first, uint32_t count, uint8_t *out64) {
+    ABI_TRY
+    require_ready();
+    if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    CurveCtx &cc = c.curve[curve];
+    if (log_n == 0 || log_n > 30 || (1u << log_n) > cc.depth) throw std::runtime_error("lagrange: domain larger than the resident SRS");
+    if ((uint64_t)first + count > (1ull << log_n)) throw std::runtime_error("lagrange: index out of the domain");
+    if (!count) return 0;
+    const int sfield = curve == 1 ? 0 : 1;
+    fe omega_inv, n_inv;
+    if (sfield == 0)
+        lagrange_consts<FpParams>(log_n, omega_inv, n_inv);
+    else
+        lagrange_consts<FqParams>(log_n, omega_inv, n_inv);
+    AbiScratch &sc = scratch();
+    const uint32_t n = 1u << log_n;
+    // rows of scalars in chunks of at most 64 commitments (64 x 2^14 x 32 B = 32 MiB)
+    const uint32_t chunk = std::max<uint32_t>(1, std::min<uint32_t>(count, (1u << 20) / n ? (1u << 20) / n : 1));
+    fe *d_sc = reinterpret_cast<fe *>(sc.scalars[0].reserve((size_t)chunk * n * 8));
+    affine *out = sc.out.reserve(chunk);
+    uint32_t *can = sc.out_can.reserve((size_t)chunk * 16);
+    cc.fixed->enable_kernel_timing(false);
+    for (uint32_t done = 0; done < count; done += chunk) {
+        const uint32_t cur = std::min(chunk, count - done);
+        launch_lagrange_scalars(sfield, omega_inv, n_inv, (int)log_n, first + done, cur, d_sc, c.stream);
+        cc.fixed->run(reinterpret_cast<const uint32_t *>(d_sc), cur, n, out, c.stream);
+        launch_affine_from_mont(curve, out, can, cur, c.stream);
+        c.launches += 2;
+        CTX_CUDA_OK(cudaMemcpyAsync(out64 + 64 * (size_t)done, can, 64 * (size_t)cur, cudaMemcpyDeviceToHost, c.stream));
+        CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    }
+    if (cc.fixed->take_error(c.stream)) throw std::runtime_error("lagrange: scalar overflow flagged by the MSM engine");
     return 0;
     ABI_CATCH
 }

@@ -104,3 +104,17 @@ void launch_fe_from_mont(int field, const fe *d_in, fe *d_out, uint32_t n, cudaS
 }
 
 }  // namespace pasta
+
+namespace pasta {
+void launch_lagrange_scalars(int field, const fe &omega_inv_mont, const fe &n_inv_mont, int log_n, uint32_t first, uint32_t count, fe *d_out,
+                             cudaStream_t s) {
+    if (field != 0 && field != 1) throw std::runtime_error("bad field id");
+    const uint64_t total = (uint64_t)count << log_n;
+    if (!total) return;
+    dim3 g((unsigned)((total + 255) / 256));
+    if (field == 0)
+        k_lagrange_scalars<FpParams><<<g, 256, 0, s>>>(omega_inv_mont, n_inv_mont, log_n, first, count, d_out);
+    else
+        k_lagrange_scalars<FqParams><<<g, 256, 0, s>>>(omega_inv_mont, n_inv_mont, log_n, first, count, d_out);
+}
+}  // namespace pasta

@@ -179,6 +179,26 @@ __global__ void __launch_bounds__(128) k_combined_inner_product(const fe *__rest
     out[p] = acc;
 }
 
+// Coefficients of the Lagrange polynomials of the radix-2 domain of size n = 2^log_n (kimchi `add_lagrange_basis`,
+// AL/operator/mina/lib/src/verifier_index.rs:204-208):  L_i(x) = (1/n) sum_j omega^(-i j) x^j, so the commitment of
+// L_i is the MSM of row i below over g[0..n).  out: [count][n] canonical; omega_inv, n_inv: Montgomery.
+template <class S>
+__global__ void __launch_bounds__(256) k_lagrange_scalars(fe omega_inv, fe n_inv, int log_n, uint32_t first, uint32_t count,
+                                                          fe *__restrict__ out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = 1u << log_n;
+    if (idx >= (uint64_t)count * n) return;
+    const uint32_t i = first + (uint32_t)(idx >> log_n), j = (uint32_t)(idx & (n - 1));
+    // omega^(-i j): the exponent only matters mod n
+    const uint32_t e = (uint32_t)(((uint64_t)i * j) & (n - 1));
+    fe acc = Fd<S>::one(), base = omega_inv;
+    for (int b = 0; b < log_n; b++) {
+        if ((e >> b) & 1u) acc = Fd<S>::mul(acc, base);
+        base = Fd<S>::sqr(base);
+    }
+    out[idx] = Fd<S>::from_mont(Fd<S>::mul(acc, n_inv));
+}
+
 // canonical <-> Montgomery for flat arrays of field elements
 template <class S>
 __global__ void __launch_bounds__(256) k_fe_to_mont(const fe *__restrict__ in, fe *__restrict__ out, uint32_t n) {
@@ -203,6 +223,8 @@ void launch_bpoly_eval(int field, const fe *d_chals, const fe *d_x, fe *d_out, u
                        cudaStream_t s);
 void launch_combined_inner_product(int field, const fe *d_evals, const fe *d_scales, fe *d_out, uint32_t nproofs, uint32_t npolys,
                                    uint32_t npts, cudaStream_t s);
+void launch_lagrange_scalars(int field, const fe &omega_inv_mont, const fe &n_inv_mont, int log_n, uint32_t first, uint32_t count, fe *d_out,
+                             cudaStream_t s);
 void launch_fe_to_mont(int field, const fe *d_in, fe *d_out, uint32_t n, cudaStream_t s);
 void launch_fe_from_mont(int field, const fe *d_in, fe *d_out, uint32_t n, cudaStream_t s);
 

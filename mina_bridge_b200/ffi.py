@@ -62,6 +62,13 @@ def srs_points(curve: int, first: int, count: int, want_h: bool = False):
     return (out.raw, h.raw) if want_h else out.raw
 
 
+def lagrange_commitments(curve: int, log_n: int, first: int, count: int) -> list[bytes]:
+    """Commitments of the Lagrange polynomials L_first.. of the 2^log_n domain over the resident SRS (canonical affine)."""
+    out = ctypes.create_string_buffer(64 * max(count, 1))
+    _check(load().mina_b200_lagrange_commitments(curve, ctypes.c_uint32(log_n), ctypes.c_uint32(first), ctypes.c_uint32(count), out))
+    return [out.raw[64 * i : 64 * i + 64] for i in range(count)]
+
+
 def msm_srs(curve: int, scalars: bytes, n: int) -> list[bytes]:
     """nmsm MSMs over the resident SRS prefix g[0..n); returns canonical affine results."""
     assert n == 0 or len(scalars) % (32 * n) == 0

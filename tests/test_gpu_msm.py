@@ -175,3 +175,32 @@ def test_msm_full_depth_random_and_linearity(gpu):
         want, _ = cref.msm(cid, cref.ints_to_bytes(a), gpu.srs_points(cid, 0, n), 8)
         assert ra == want
         assert pasta.add(cref.bytes_to_point(ra), cref.bytes_to_point(rb), fm) == cref.bytes_to_point(rab)
+
+
+def test_lagrange_commitments_match_the_oracle(gpu):
+    """a5: kimchi `add_lagrange_basis` over the wrap domain (2^14, Pallas; verifier_index.rs:204-208).  L_i has
+    coefficients omega^(-i j) / n with omega the domain generator of the VK (K-G): the device commitment must equal the
+    oracle MSM of those coefficients, and the basis must behave like one: sum_i L_i commits the constant 1 = g[0]."""
+    log_n, n, q = 14, 1 << 14, pasta.Q
+    omega = int("1E5587687024253BB079B38D9C5371594958E496C605D3BD898B34D068AFBEE7", 16)  # devnet_vk.json index.domain.group_gen
+    assert pow(omega, n, q) == 1 and pow(omega, n // 2, q) != 1
+    w_inv, n_inv = pow(omega, q - 2, q), pow(n, q - 2, q)
+    g = gpu.srs_points(0, 0, n)
+    idx = [0, 1, 39, n - 1]
+    got = [gpu.lagrange_commitments(0, log_n, i, 1)[0] for i in idx]
+    for i, pt in zip(idx, got):
+        coeffs, cur, step = [], n_inv, pow(w_inv, i, q)
+        for _ in range(n):
+            coeffs.append(cur)
+            cur = cur * step % q
+        want, inf = cref.msm(cref.FP, cref.ints_to_bytes(coeffs), g, 4)
+        assert not inf and pt == want, i
+    # a small domain in full: the commitments of all L_i add up to the commitment of the constant polynomial 1
+    small = gpu.lagrange_commitments(0, 4, 0, 16)
+    acc = None
+    for pt in small:
+        acc = pasta.add(acc, cref.bytes_to_point(pt), pasta.P)
+    assert acc == cref.bytes_to_point(g[:64])
+    # and the 40 the verifier uses come out in one call, equal to the single calls
+    first40 = gpu.lagrange_commitments(0, log_n, 0, 40)
+    assert first40[0] == got[0] and first40[1] == got[1] and first40[39] == got[2]
