@@ -524,6 +524,65 @@ def bench_ipa(a, torch, dist, mb, rank, world, dev):
             "gpu_launches": int(launches), "clocks": sampler.summary()}
 
 
+def bench_merkle(a, torch, dist, mb, rank, world, dev):
+    """K3 alone: BATCH Merkle paths of the account fixture's shape (35 levels) folded with Poseidon through
+    mina_b200_merkle_fold.  The table is arbitrary (kimchi constants unavailable): the work does not depend on it."""
+    import random
+
+    P = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
+    rng = random.Random(CORRUPT_SEED)
+    table = b"".join(rng.randrange(P).to_bytes(32, "little") for _ in range(174))
+    depth = 35
+    n = BATCH // world
+    paths = [[(rng.randrange(2), rng.randrange(P)) for _ in range(depth)] for _ in range(n)]
+    leaves = [rng.randrange(P) for _ in range(n)]
+    _, roots = mb.merkle_fold(table, paths, leaves, [0] * n)  # the device's own roots: a second fold must reproduce them
+    bad = {i for i in corrupt_positions() if i < n}
+    want_roots = [(r + 1) % P if i in bad else r for i, r in enumerate(roots)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ok, _ = mb.merkle_fold(table, paths, leaves, want_roots)
+    assert ok == [0 if i in bad else 1 for i in range(n)]
+    W = max(a.warmup, 3)
+    for _ in range(W):
+        mb.merkle_fold(table, paths, leaves, want_roots)
+    sampler = ClockSampler()
+    sampler.start()
+    l0 = mb.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        mb.merkle_fold(table, paths, leaves, want_roots)
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    launches = mb.launch_count() - l0
+    sampler.stop.set()
+    sampler.join()
+    if a.profile_step:
+        barrier()
+        torch.cuda.profiler.start()
+        mb.merkle_fold(table, paths, leaves, want_roots)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    if rank != 0:
+        return None
+    v = n * world * a.steps / float(t.item())
+    return {"metric": "merkle_paths_per_sec", "value": v, "unit": "paths/s (35 levels)", "n_gpus": world, "steps": a.steps, "warmup": W,
+            "ms_per_step": float(t.item()) / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u256 modular (8x32 Montgomery)", "data": "synthetic",
+            "config": {"workload": "merkle%d: verify_merkle_proof over %d paths of 35 levels per step (Python list marshalling included in the time)" % (BATCH, BATCH),
+                       "value_is_e2e": True, "poseidon_table": "arbitrary (kimchi constants unavailable): parity unpinned, timing unaffected"},
+            "roofline": None,
+            "e2e": {"value": v, "unit": "paths/s (35 levels)", "h2d_bytes_per_step": n * (35 * 48 + 68), "d2h_bytes_per_step": n * 33},
+            "gpu_launches": int(launches), "clocks": sampler.summary()}
+
+
 def bench_mixed(a, torch, dist, mb, rank, world, dev):
     """BASELINE configs[4]: BATCH/2 proof-of-state + BATCH/2 proof-of-account inputs per step through the two batch entry
     points (host buffers in, result bytes out, one all-reduce(MIN)).  Built stages only: see config.absent_stages."""
@@ -611,7 +670,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20", "ipa", "mixed"])
+    ap.add_argument("--workload", default="state1024", choices=["state1024", "msm20", "ipa", "mixed", "merkle"])
     ap.add_argument("--profile-step", default="", choices=["", "rlc", "per_proof"],
                     help="run one extra untimed step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off)")
     ap.add_argument("--batch", type=int, default=BATCH, help="proofs per step (default: the 1024 of BASELINE.json; 64 = configs[2])")
@@ -640,7 +699,7 @@ def main():
         dist.barrier()
     mb.init(local)
     dev = torch.device("cuda", local)
-    line = {"state1024": bench_state, "msm20": bench_msm20, "ipa": bench_ipa, "mixed": bench_mixed}[a.workload](a, torch, dist, mb, rank, world, dev)
+    line = {"state1024": bench_state, "msm20": bench_msm20, "ipa": bench_ipa, "mixed": bench_mixed, "merkle": bench_merkle}[a.workload](a, torch, dist, mb, rank, world, dev)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -22,76 +22,6 @@
 
 namespace pasta {
 
-// ---- Fq-sponge, four lanes per opening (lanes 0..2 hold one state element each, lane 3 idles) ------------------
-// One permutation is 55 dependent rounds; with the three S-boxes and the three MDS rows of a round on three
-// lanes a round is 7 dependent multiplications instead of 21.
-template <class F>
-struct LaneSponge {
-    fe st;            // this lane's state element, Montgomery
-    bool absorbing;   // SpongeState::Absorbed(count) / Squeezed(count); uniform across the warp
-    int count;
-    const fe *tab;    // 9 MDS + 165 round constants, Montgomery
-    uint32_t lane;    // 0..3 inside the group
-    uint32_t base;    // first lane of the group inside the warp
-
-    __device__ __forceinline__ fe from_lane(const fe &v, int l) const {
-        fe r;
-#pragma unroll
-        for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], base + l);
-        return r;
-    }
-    __device__ void permute() {
-        const uint32_t row = lane < 3 ? lane : 0;
-#pragma unroll 1
-        for (int r = 0; r < POSEIDON_ROUNDS; r++) {
-            fe x2 = Fd<F>::sqr(st), x4 = Fd<F>::sqr(x2);
-            fe sb = Fd<F>::mul(Fd<F>::mul(x4, x2), st);
-            fe s0 = from_lane(sb, 0), s1 = from_lane(sb, 1), s2 = from_lane(sb, 2);
-            fe acc = Fd<F>::mul(tab[3 * row], s0);
-            acc = Fd<F>::add(acc, Fd<F>::mul(tab[3 * row + 1], s1));
-            acc = Fd<F>::add(acc, Fd<F>::mul(tab[3 * row + 2], s2));
-            st = Fd<F>::add(acc, tab[9 + 3 * r + row]);
-        }
-    }
-    // x: Montgomery, the same value on every lane of the group
-    __device__ void absorb(const fe &x) {
-        int slot;
-        if (absorbing) {
-            if (count == 2) {
-                permute();
-                slot = 0;
-                count = 1;
-            } else {
-                slot = count;
-                count++;
-            }
-        } else {
-            slot = 0;
-            absorbing = true;
-            count = 1;
-        }
-        if ((int)lane == slot) st = Fd<F>::add(st, x);
-    }
-    // returns the squeezed element (Montgomery) on every lane of the group
-    __device__ fe squeeze() {
-        int slot;
-        if (absorbing) {
-            permute();
-            absorbing = false;
-            count = 1;
-            slot = 0;
-        } else if (count == 2) {
-            permute();
-            count = 1;
-            slot = 0;
-        } else {
-            slot = count;
-            count++;
-        }
-        return from_lane(st, slot);
-    }
-};
-
 // One opening per 4 lanes.  Inputs canonical; outputs: t (canonical base-field element for to_group) and k + 1
 // 128-bit prechallenges (k rounds, then the one for c).
 //   absorb_fr(shift_scalar(cip)); t = challenge_fq(); for each (L, R): absorb_g(L), absorb_g(R), challenge();

@@ -20,11 +20,11 @@ void launch_merkle_fold(int field, const fe *d_tab, const fe *d_prefix_states, c
                         cudaStream_t s) {
     if (field != 0 && field != 1) throw std::runtime_error("bad field id");
     if (!nproofs) return;
-    dim3 g((nproofs + 63) / 64);
+    dim3 g((4 * nproofs + 127) / 128);  // four lanes per path
     if (field == 0)
-        k_merkle_fold<FpParams><<<g, 64, 0, s>>>(d_tab, d_prefix_states, d_nodes, d_depths, max_depth, d_leaves, d_roots, d_ok, d_folded, nproofs);
+        k_merkle_fold<FpParams><<<g, 128, 0, s>>>(d_tab, d_prefix_states, d_nodes, d_depths, max_depth, d_leaves, d_roots, d_ok, d_folded, nproofs);
     else
-        k_merkle_fold<FqParams><<<g, 64, 0, s>>>(d_tab, d_prefix_states, d_nodes, d_depths, max_depth, d_leaves, d_roots, d_ok, d_folded, nproofs);
+        k_merkle_fold<FqParams><<<g, 128, 0, s>>>(d_tab, d_prefix_states, d_nodes, d_depths, max_depth, d_leaves, d_roots, d_ok, d_folded, nproofs);
 }
 
 }  // namespace pasta
