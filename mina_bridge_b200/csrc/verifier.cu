@@ -96,19 +96,40 @@ static bool point_on_curve(const wire::Point &p) {
     a.inf = false;
     return a.on_curve();  // (0,0) is not on y^2 = x^3 + 5, so the identity encoding is rejected too
 }
+static void random_bytes(uint8_t *out, size_t n) {
+    size_t got = 0;
+    while (got < n) {
+        ssize_t r = getrandom(out + got, std::min<size_t>(n - got, 256), 0);  // <= 256 bytes never returns short
+        if (r <= 0) throw std::runtime_error("getrandom failed");
+        got += (size_t)r;
+    }
+}
+// one non-zero 128-bit value, zero-extended to a 32-byte little-endian field element
 static void random_128(uint8_t *out32) {
     std::memset(out32, 0, 32);
     for (;;) {
-        size_t got = 0;
-        while (got < 16) {
-            ssize_t r = getrandom(out32 + got, 16 - got, 0);
-            if (r <= 0) throw std::runtime_error("getrandom failed");
-            got += (size_t)r;
-        }
+        random_bytes(out32, 16);
         uint64_t lo, hi;
         std::memcpy(&lo, out32, 8);
         std::memcpy(&hi, out32 + 8, 8);
         if (lo | hi) return;
+    }
+}
+// n of them, one system call per 16 values
+static void random_128_array(uint8_t *out32, size_t n) {
+    uint8_t buf[256];
+    for (size_t i = 0; i < n; i += 16) {
+        const size_t cnt = std::min<size_t>(16, n - i);
+        random_bytes(buf, 16 * cnt);
+        for (size_t k = 0; k < cnt; k++) {
+            uint8_t *o = out32 + 32 * (i + k);
+            std::memset(o, 0, 32);
+            std::memcpy(o, buf + 16 * k, 16);
+            uint64_t lo, hi;
+            std::memcpy(&lo, o, 8);
+            std::memcpy(&hi, o + 8, 8);
+            if (!(lo | hi)) random_128(o);
+        }
     }
 }
 
@@ -662,7 +683,7 @@ static void acc_rlc(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &a
     const int field = ab.curve == 1 ? 0 : 1;
     AccDevice dv = acc_prepare(c, rs, sb, ab);
     uint8_t *h_r = sb.h_r.reserve((size_t)ab.m * 32);
-    for (uint32_t i = 0; i < ab.m; i++) random_128(h_r + 32 * (size_t)i);
+    random_128_array(h_r, ab.m);
     fe *d_r_can = sb.d_r_can.reserve(ab.m), *d_r = sb.d_r.reserve(2 * (size_t)ab.m);
     RlcBatch rb;
     rlc_buffers(sb, ab, rb);
