@@ -273,6 +273,31 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
     t_dev, kms = timed(lambda: step_device(mb.MODE_RLC, True), a.steps)
     launches = mb.launch_count() - l0
     t_e2e, _ = timed(lambda: step_e2e(mb.MODE_RLC), a.steps)
+    # two host threads submitting batches back to back (what the operator's goroutines do): the host pass of one batch
+    # (decode, checks, packing) overlaps the device work of the other; only rank-local, no reduction inside the callers
+    def two_callers():
+        errs = []
+
+        def worker():
+            try:
+                for _ in range(a.steps):
+                    mb.verify_state_stages(hp, hq, mb.MODE_RLC)
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        ts = [threading.Thread(target=worker) for _ in range(2)]
+        barrier()
+        t0 = time.perf_counter()
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert not errs, errs
+        return 2 * a.steps * BATCH / float(dt.item())
+
+    e2e_concurrent = two_callers()
     pp_steps = max(2, min(a.steps, 4))
     t_pp, kms_pp = timed(lambda: step_device(mb.MODE_PER_PROOF, True), pp_steps)
     t_pp_e2e, _ = timed(lambda: step_e2e(mb.MODE_PER_PROOF), pp_steps)
@@ -362,6 +387,7 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
                          "sample": "2 proofs of the batch (all cores) + 1 proof (one thread), per-proof MSMs; oracle/pasta_ref.c (arkworks window rule c = ln n + 2, 1 thread/window, unrolled 4x64 CIOS) + Python decoder; NOT the reference binary. modmul_ns is the port's dependent-chain latency on this host; arkworks with the x86 asm backend is usually quoted at 20-25 ns, so the real reference is likely 2-3x faster than this port"},
         "e2e": {"value": BATCH * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": m * (256 + 64 + 480 + 128 + 3 * 32) + m,
                 "d2h_bytes_per_step": 2 * 128 + BATCH,
+                "two_concurrent_callers": e2e_concurrent,
                 "note": "host buffers = %d x 48 342 B serialized proofs + 1 057 B pub inputs read by host threads; only the extracted prechallenges / points / RLC scalars cross PCIe" % m},
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
