@@ -3,22 +3,26 @@
 
 Default workload `state1024` (BASELINE.json: "1024-proof Mina-state batch"): one STEP verifies a fixed
 batch of 1024 serialized proof-of-state inputs (the reference's own fixture replicated, 1 % of them
-with one flipped bit in an IPA prechallenge) through every stage this build has -- bincode decode,
-the plain-comparison half of check_pub_inputs, the fork-choice rule, accumulator_check (Vesta 2^16)
-and the wrap proof's two previous-challenge accumulators (Pallas 2^15).  The batch is strong-scaled:
-rank r takes proofs i = r (mod N); the per-proof result bytes are combined with ONE NCCL
-all-reduce(MIN) inside the timed region (AL/operator/pkg/operator.go:461-465).
+with one flipped bit in an IPA prechallenge, at seeded random positions) through every stage this build
+has -- bincode decode, the plain-comparison half of check_pub_inputs, the fork-choice rule,
+accumulator_check (Vesta 2^16) and the wrap proof's two previous-challenge accumulators (Pallas 2^15).
+The batch is strong-scaled: rank r takes proofs i = r (mod N); the per-proof result bytes are combined
+with ONE NCCL all-reduce(MIN) inside the timed region (AL/operator/pkg/operator.go:461-465).
 
-READ `config.absent_stages`: the kimchi transcript / IPA final check and the 17 Poseidon state hashes
-are NOT built (Poseidon constants unavailable => parity unpinned), so the full
-accept bit is always 0 and the byte that is reduced is "every built stage passed".  The metric is named
-for what it is.
+READ `config.absent_stages`: the kimchi transcript and the 17 Poseidon state hashes are NOT built
+(Poseidon constants unavailable => parity unpinned), so the full accept bit is
+always 0 and the byte that is reduced is "every built stage passed".  The metric is named for what it is.
 
   value  = proofs/s with the per-proof device inputs (prechallenges + accumulator points) resident in HBM
   e2e    = proofs/s through the C ABI with HOST buffers holding the serialized proofs (decode on host
            threads, pinned staging, H2D, kernels, D2H of the result bytes all inside the timed region)
-Other workloads: --workload msm20 (BASELINE config 2: one 2^20-point Vesta MSM over resident bases),
---workload accmsm (round-1 line: 64 per-proof 2^16 MSMs with uploaded scalars).
+Other workloads (same JSON schema; none is the driver's default):
+  --workload msm20   BASELINE configs[1]: one 2^20-point Vesta MSM over resident bases
+  --batch 64         BASELINE configs[2]'s batch size through the default workload
+  --workload mixed   BASELINE configs[4]: 512 proof-of-state + 512 proof-of-account inputs
+  --workload ipa     row a9 alone: 1024 IPA final checks of the wrap proof's shape (oracle-made fixture)
+  --workload merkle  K3 alone: 1024 Merkle paths of 35 levels
+  --profile-step rlc wraps ONE extra untimed step in cudaProfilerStart/Stop (ncu --profile-from-start off)
 """
 from __future__ import annotations
 
