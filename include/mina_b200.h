@@ -237,6 +237,11 @@ int mina_b200_host_vk_load(const char *path, uint8_t *out, uint32_t meta[4]);
 /* Host Poseidon sponge: hash_with_kimchi(prefix, xs[0..n)) with the given table (Fp). */
 int mina_b200_host_hash_with_kimchi(const uint8_t *table, const char *prefix, const uint8_t *xs32, uint32_t n, uint8_t out32[32]);
 int mina_b200_host_poseidon_permute(int field, const uint8_t *table, uint32_t n, uint8_t *states96);
+/* The planner of the batched checks' group testing (csrc/group_testing.hpp) against a simulated device: bad[i] != 0
+ * marks the bad items of a batch of m.  ok_out[i] receives the bit the batched check would report; *levels and *msms the
+ * number of sequential levels and of MSM evaluations over the resident SRS it would cost.  -1 on an internal
+ * inconsistency (see last_error). */
+int mina_b200_host_group_testing_sim(uint32_t m, const uint8_t *bad, uint8_t *ok_out, uint32_t *levels, uint32_t *msms);
 /* Wire encoders (csrc/wire_write.hpp; the producer side, core/src/aligned.rs:33-49): decode `data` as `kind`
  * (same ids as mina_b200_host_decode) and encode it again.  *out_len in = capacity, out = bytes written.
  * Returns 0, -1 decode error, -2 not re-encodable / buffer too small. */

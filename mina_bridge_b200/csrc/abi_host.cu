@@ -7,6 +7,7 @@
 #include "../../include/mina_b200.h"
 #include "consensus.hpp"
 #include "context.cuh"
+#include "group_testing.hpp"
 #include "sol_account.hpp"
 #include "wire.hpp"
 #include "wire_write.hpp"
@@ -307,6 +308,21 @@ static int emit_bytes(const std::vector<uint8_t> &enc, uint8_t *out, size_t *out
     if (!enc.empty()) std::memcpy(out, enc.data(), enc.size());
     *out_len = enc.size();
     return 0;
+}
+
+int mina_b200_host_group_testing_sim(uint32_t m, const uint8_t *bad, uint8_t *ok_out, uint32_t *levels, uint32_t *msms) {
+    try {
+        std::vector<uint8_t> b(bad, bad + m), ok;
+        uint32_t n_msm = 0;
+        uint32_t lv = m ? gt::simulate(m, b, ok, n_msm) : 0;
+        if (m) std::memcpy(ok_out, ok.data(), m);
+        if (levels) *levels = lv;
+        if (msms) *msms = n_msm;
+        return 0;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return -1;
+    }
 }
 
 int mina_b200_host_reencode(int kind, const uint8_t *data, size_t len, uint8_t *out, size_t *out_len) {

@@ -30,6 +30,7 @@
 #include "../../include/mina_verifier.h"
 #include "consensus.hpp"
 #include "context.cuh"
+#include "group_testing.hpp"
 #include "ipa.cuh"
 #include "ipa_verify.cuh"
 #include "poseidon.cuh"
@@ -37,6 +38,9 @@
 #include "wire.hpp"
 
 namespace pasta {
+using gt::COMBINE_SLICE;
+using gt::LevelGroup;
+using gt::LevelPlan;
 
 // ---- persistent staging ---------------------------------------------------------------------------
 struct SideBuffers {  // one accumulator family (Vesta k=16 or Pallas k=15)
@@ -462,35 +466,6 @@ static __global__ void __launch_bounds__(LOCATE_THREADS) k_locate(const xyzz *__
 // bad proof is resolved by one test instead of log2(size) halvings; a group with more is split (wide while few
 // groups are open, so the launch set fills the GPU; at slice boundaries while groups are large).  The last
 // child of every split needs no MSM (A_last = A_parent - siblings).
-static constexpr uint32_t COMBINE_SLICE = 64;
-// open groups x children per level the splits aim for (MINA_B200_SPLIT_TARGET overrides it: tuning only)
-static uint32_t split_target() {
-    static const uint32_t v = [] {
-        const char *e = std::getenv("MINA_B200_SPLIT_TARGET");
-        int x = e ? std::atoi(e) : 0;
-        return (uint32_t)(x >= 2 && x <= 64 ? x : 4);  // 4: best of {2..32} on 1024/10, 128/2, 1024/30, 1024/100 (tools/sweep_split.sh)
-    }();
-    return v;
-}
-struct LevelGroup {
-    uint32_t a = 0, b = 0;
-    uint32_t parent = 0;  // index into the previous level's group list
-    uint32_t size() const { return b - a; }
-};
-struct LevelPlan {
-    // groups in result order: MSM groups built from kept slices, MSM groups combined from tables, derived groups
-    std::vector<LevelGroup> sliced, combined, derived;
-    std::vector<std::array<uint32_t, 3>> derived_meta;  // parent, sibling range in MSM order
-    size_t n_msm() const { return sliced.size() + combined.size(); }
-    size_t size() const { return n_msm() + derived.size(); }
-    const LevelGroup &at(size_t g) const {
-        if (g < sliced.size()) return sliced[g];
-        g -= sliced.size();
-        return g < combined.size() ? combined[g] : derived[g - combined.size()];
-    }
-};
-static bool slice_aligned(const LevelGroup &g, uint32_t m) { return g.a % COMBINE_SLICE == 0 && (g.b % COMBINE_SLICE == 0 || g.b == m); }
-
 // What stays on the device for the whole batch
 struct RlcBatch {
     fe *d_tab = nullptr, *d_tab_w = nullptr;          // product tables: hi scaled by r_j / by (j + 1) r_j
@@ -652,19 +627,6 @@ static void combine_slices(Context &c, AccRun &rs, SideBuffers &sb, const Accumu
     }
 }
 
-// children of an unresolved group [a, b): `t` parts, cut at slice boundaries while the parts are larger than a slice
-static std::vector<uint32_t> split_points(uint32_t a, uint32_t b, uint32_t t) {
-    const uint32_t size = b - a;
-    uint32_t part = (size + t - 1) / t;
-    if (part > COMBINE_SLICE) part = (part + COMBINE_SLICE - 1) / COMBINE_SLICE * COMBINE_SLICE;
-    std::vector<uint32_t> cuts;
-    uint32_t first = part;
-    if (part > COMBINE_SLICE && a % COMBINE_SLICE) first = part - a % COMBINE_SLICE;  // land on slice boundaries
-    for (uint32_t cut = a + first; cut < b; cut += part) cuts.push_back(cut);
-    if (cuts.empty()) cuts.push_back(a + (size + 1) / 2);
-    return cuts;
-}
-
 static void rlc_levels(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab, RlcBatch &rb, const fe *d_chal, fe *d_r,
                        const uint32_t *h_bad);
 static void rlc_buffers(SideBuffers &sb, const AccumulatorBatch &ab, RlcBatch &rb) {
@@ -749,54 +711,8 @@ static void rlc_levels(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch
             plan = std::move(next);
             continue;
         }
-        // verdicts; unresolved groups are split next
-        std::vector<uint32_t> open;
-        for (size_t g = 0; g < plan.size(); g++) {
-            const LevelGroup &grp = plan.at(g);
-            if (status[g] == 1) {
-                for (uint32_t i = grp.a; i < grp.b; i++) ab.ok[i] = 1;
-            } else if (status[g] >= 2) {
-                const uint32_t bad = status[g] - 2;
-                if (bad < grp.a || bad >= grp.b) throw std::runtime_error("accumulator check: locator returned an index outside its group");
-                for (uint32_t i = grp.a; i < grp.b; i++) ab.ok[i] = i == bad ? 0 : 1;
-            } else if (grp.size() <= 2) {
-                for (uint32_t i = grp.a; i < grp.b; i++) ab.ok[i] = 0;  // not "none" and not "exactly one": every member is bad
-            } else {
-                open.push_back((uint32_t)g);
-            }
-        }
-        if (open.empty()) break;
-        const uint32_t target = split_target();
-        const uint32_t t = std::max<uint32_t>(2, std::min<uint32_t>(target, (target + (uint32_t)open.size() - 1) / (uint32_t)open.size()));
-        struct Pending {
-            uint32_t parent, list, begin, end;  // siblings [begin, end) inside list 0 (sliced) or 1 (combined)
-        };
-        std::vector<Pending> pend;
-        for (uint32_t g : open) {
-            const LevelGroup &grp = plan.at(g);
-            std::vector<uint32_t> cuts = split_points(grp.a, grp.b, std::min(t, grp.size()));
-            // the MSM children of one parent all go to the same list so that they stay adjacent
-            bool all_sliced = true;
-            uint32_t lo = grp.a;
-            for (uint32_t cut : cuts) {
-                all_sliced = all_sliced && slice_aligned(LevelGroup{lo, cut, g}, ab.m);
-                lo = cut;
-            }
-            std::vector<LevelGroup> &list = all_sliced ? next.sliced : next.combined;
-            Pending pd{g, all_sliced ? 0u : 1u, (uint32_t)list.size(), 0};
-            lo = grp.a;
-            for (uint32_t cut : cuts) {
-                list.push_back(LevelGroup{lo, cut, g});
-                lo = cut;
-            }
-            pd.end = (uint32_t)list.size();
-            pend.push_back(pd);
-            next.derived.push_back(LevelGroup{lo, grp.b, g});
-        }
-        for (const Pending &pd : pend) {
-            const uint32_t shift = pd.list ? (uint32_t)next.sliced.size() : 0u;
-            next.derived_meta.push_back({pd.parent, pd.begin + shift, pd.end + shift});
-        }
+        // verdicts; unresolved groups are split next (group_testing.hpp)
+        if (!gt::plan_next_level(plan, status, ab.m, ab.ok, next)) break;
         plan = std::move(next);
     }
 }

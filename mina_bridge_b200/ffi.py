@@ -402,6 +402,16 @@ def _host_bytes_out(fn, *args, cap=1 << 17):
     return (buf.raw[:n.value] if rc == 0 else None), rc
 
 
+def host_group_testing_sim(bad: bytes):
+    """The group-testing planner against a simulated device.  bad: one byte per item (non-zero = bad).
+    Returns (ok bytes, levels, msms)."""
+    m = len(bad)
+    ok = ctypes.create_string_buffer(max(m, 1))
+    lv, ms = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    _check(load().mina_b200_host_group_testing_sim(ctypes.c_uint32(m), bad, ok, ctypes.byref(lv), ctypes.byref(ms)))
+    return ok.raw[:m], lv.value, ms.value
+
+
 def host_reencode(kind: int, data: bytes):
     """decode + encode through the C++ wire writers (csrc/wire_write.hpp).  None on a decode error."""
     lib = load()

@@ -124,3 +124,30 @@ def test_srs_file_loader_on_the_reference_files_when_present(native):
             pytest.skip("reference tree not mounted")
         g, h = native.host_srs_load_file(cid, path, depth)
         assert hashlib.sha256(g).hexdigest() == pins[name]["sha256_g_%d" % depth] and h.hex() == pins[name]["h"]
+
+
+# ---- group testing planner (csrc/group_testing.hpp) against a simulated device -------------------------------------
+def test_group_testing_planner_resolves_every_pattern(native):
+    """The host logic that drives the batched accumulator / IPA checks: with the device replaced by the truth (a group
+    reports "all good", "exactly one bad: index j" or "two or more bad"), every index must come out with the right bit,
+    for every batch size and corruption pattern, within a bounded number of levels and MSMs.  The simulator also checks
+    the structure the device path relies on (children tile their parent, sibling ranges, derived child closes it)."""
+    rng = random.Random(0x4D494E41)
+    worst = {}
+    for m in [1, 2, 3, 4, 5, 7, 8, 63, 64, 65, 100, 127, 128, 129, 130, 200, 333, 512, 1000, 1024, 1500, 2048]:
+        patterns = [set(), {0}, {m - 1}, {m // 2}, set(range(m)), set(range(0, m, 2)), set(range(min(m, 64))), {0, m - 1}]
+        patterns += [set(rng.sample(range(m), min(m, k))) for k in (2, 3, 10, 30) for _ in range(3)]
+        patterns += [{i for i in range(m) if 60 <= i % 64 or i % 64 < 3}]  # clusters across every slice boundary
+        for bad in patterns:
+            flags = bytes(1 if i in bad else 0 for i in range(m))
+            ok, levels, msms = native.host_group_testing_sim(flags)
+            assert ok == bytes(0 if i in bad else 1 for i in range(m)), (m, sorted(bad)[:8])
+            k = len(bad)
+            if k == 0:
+                assert (levels, msms) == (1, 1)
+            elif k == 1 and m > 1:
+                assert (levels, msms) == (2, 3)  # one failing level 0, one locator level over the whole batch
+            # never worse than testing every item on its own twice over, and logarithmic depth
+            assert msms <= 1 + 2 * max(m, 2) and levels <= 2 + 2 * max(1, m).bit_length()
+            worst[(m, k)] = max(worst.get((m, k), 0), msms)
+    assert worst[(1024, 10)] <= 60  # the bench's shape costs ~28 on its seeded pattern
