@@ -237,9 +237,10 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
     hp, hq = mb.Batch(my_proofs), mb.Batch(my_pubs)
 
     def step_e2e(mode):
-        _, reps = mb.verify_state_stages(hp, hq, mode)
-        bits = bytes(int(r.failed == 0 and (r.passed & built) == built) for r in reps)
-        return reduce_bits(bits)
+        rep = mb.verify_state_stage_masks(hp, hq, mode)  # (m, 3) uint32: passed, failed, unavailable
+        bits = ((rep[:, 1] == 0) & ((rep[:, 0] & built) == built)).astype(np.uint8)
+        pin.copy_(torch.from_numpy(bits))
+        return shard.merge_result_bytes(torch, dist, result, idx, pin.to(dev, non_blocking=True), world)
 
     def barrier():
         if world > 1:
@@ -285,7 +286,7 @@ def bench_state(a, torch, dist, mb, rank, world, dev):
         def worker():
             try:
                 for _ in range(a.steps):
-                    mb.verify_state_stages(hp, hq, mb.MODE_RLC)
+                    mb.verify_state_stage_masks(hp, hq, mb.MODE_RLC)
             except Exception as e:  # pragma: no cover
                 errs.append(e)
 
