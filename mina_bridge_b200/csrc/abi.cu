@@ -756,6 +756,9 @@ __global__ void k_field_op(int op, uint32_t n, const fe *a, const fe *b, fe *out
 #ifdef __CUDA_ARCH__
             case 16: r0 = Fd<F>::mul_ptx(a[i], b[i]); break;   // first-generation multiplier
             case 17: r0 = Fd<F>::mul_ptx2(a[i], b[i]); break;  // IMAD.WIDE-chain reduction (the default)
+            // sums of products with one reduction (lazy reduction): elements i, i+1, i+2 (cyclically)
+            case 18: r0 = Fd<F>::dot2(a[i], b[i], a[(i + 1) % n], b[(i + 1) % n]); break;
+            case 19: r0 = Fd<F>::dot3(a[i], b[i], a[(i + 1) % n], b[(i + 1) % n], a[(i + 2) % n], b[(i + 2) % n]); break;
 #endif
 #ifdef __CUDA_ARCH__
             case 20: case 21: {

@@ -62,7 +62,7 @@ struct Ec {
         fe X2 = fd::sqr(q.x);
         fe M = fd::add(fd::dbl(X2), X2);
         r.x = fd::sub(fd::sqr(M), fd::dbl(S));
-        r.y = fd::sub(fd::mul(M, fd::sub(S, r.x)), fd::mul(W, q.y));
+        r.y = fd::dot2(M, fd::sub(S, r.x), W, fd::neg(q.y));  // difference of two products, one reduction
         r.zz = V;
         r.zzz = W;
         return r;
@@ -78,7 +78,7 @@ struct Ec {
         fe X2 = fd::sqr(p.x);
         fe M = fd::add(fd::dbl(X2), X2);
         r.x = fd::sub(fd::sqr(M), fd::dbl(S));
-        r.y = fd::sub(fd::mul(M, fd::sub(S, r.x)), fd::mul(W, p.y));
+        r.y = fd::dot2(M, fd::sub(S, r.x), W, fd::neg(p.y));
         r.zz = fd::mul(V, p.zz);
         r.zzz = fd::mul(W, p.zzz);
         return r;
@@ -106,7 +106,7 @@ struct Ec {
         fe PPP = fd::mul(P, PP);
         fe Q = fd::mul(p.x, PP);
         fe X3 = fd::sub(fd::sub(fd::sqr(R), PPP), fd::dbl(Q));
-        fe Y3 = fd::sub(fd::mul(R, fd::sub(Q, X3)), fd::mul(p.y, PPP));
+        fe Y3 = fd::dot2(R, fd::sub(Q, X3), fd::neg(p.y), PPP);
         p.x = X3;
         p.y = Y3;
         p.zz = fd::mul(p.zz, PP);
@@ -136,7 +136,7 @@ struct Ec {
         fe PPP = fd::mul(P, PP);
         fe Q = fd::mul(U1, PP);
         fe X3 = fd::sub(fd::sub(fd::sqr(R), PPP), fd::dbl(Q));
-        fe Y3 = fd::sub(fd::mul(R, fd::sub(Q, X3)), fd::mul(S1, PPP));
+        fe Y3 = fd::dot2(R, fd::sub(Q, X3), fd::neg(S1), PPP);
         p.x = X3;
         p.y = Y3;
         p.zz = fd::mul(fd::mul(p.zz, q.zz), PP);

@@ -429,8 +429,8 @@ struct Fd {
         return cond_sub_p(r);
     }
 
-    static __device__ __forceinline__ fe mul_ptx2(const fe &a, const fe &b) {
-        uint32_t X[17], Y[17];
+    // the 512-bit product in the two parity accumulators (no reduction)
+    static __device__ __forceinline__ void mul_xy(uint32_t *X, uint32_t *Y, const fe &a, const fe &b) {
 #pragma unroll
         for (int i = 8; i < 17; i++) X[i] = Y[i] = 0;
         mul_row(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
@@ -444,6 +444,69 @@ struct Fd {
                 mad_row(&X[i], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
                 mad_row(&Y[i], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
             }
+        }
+    }
+    static __device__ __forceinline__ fe mul_ptx2(const fe &a, const fe &b) {
+        uint32_t X[17], Y[17];
+        mul_xy(X, Y, a, b);
+        return redc2(X, Y);
+    }
+    // ---- lazy reduction: a sum of up to THREE products reduced once -------------------------------------------------
+    // p is 2^254 + t, so p^2 / 2^256 < p / 4 + eps: the Montgomery reduction of a sum of k products is below
+    // (k / 4 + 1) p, i.e. still under 2 p for k <= 3 and the single conditional subtraction at the end of redc2 is
+    // enough.  The reduction is 26 of the 100 multiply-pipe instructions of a product, so sums of products
+    // (k_bpoly_combine) save about a quarter of them.  (X, Y) += (X1, Y1): two full carry chains.
+    static __device__ __forceinline__ void xy_add(uint32_t *X, uint32_t *Y, const uint32_t *X1, const uint32_t *Y1) {
+        asm("add.cc.u32 %0, %0, %17;\n\t"
+            "addc.cc.u32 %1, %1, %18;\n\t"
+            "addc.cc.u32 %2, %2, %19;\n\t"
+            "addc.cc.u32 %3, %3, %20;\n\t"
+            "addc.cc.u32 %4, %4, %21;\n\t"
+            "addc.cc.u32 %5, %5, %22;\n\t"
+            "addc.cc.u32 %6, %6, %23;\n\t"
+            "addc.cc.u32 %7, %7, %24;\n\t"
+            "addc.cc.u32 %8, %8, %25;\n\t"
+            "addc.cc.u32 %9, %9, %26;\n\t"
+            "addc.cc.u32 %10, %10, %27;\n\t"
+            "addc.cc.u32 %11, %11, %28;\n\t"
+            "addc.cc.u32 %12, %12, %29;\n\t"
+            "addc.cc.u32 %13, %13, %30;\n\t"
+            "addc.cc.u32 %14, %14, %31;\n\t"
+            "addc.cc.u32 %15, %15, %32;\n\t"
+            "addc.u32 %16, %16, %33;"
+            : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(X[8]), "+r"(X[9]),
+              "+r"(X[10]), "+r"(X[11]), "+r"(X[12]), "+r"(X[13]), "+r"(X[14]), "+r"(X[15]), "+r"(X[16])
+            : "r"(X1[0]), "r"(X1[1]), "r"(X1[2]), "r"(X1[3]), "r"(X1[4]), "r"(X1[5]), "r"(X1[6]), "r"(X1[7]), "r"(X1[8]), "r"(X1[9]),
+              "r"(X1[10]), "r"(X1[11]), "r"(X1[12]), "r"(X1[13]), "r"(X1[14]), "r"(X1[15]), "r"(X1[16]));
+        asm("add.cc.u32 %0, %0, %15;\n\t"
+            "addc.cc.u32 %1, %1, %16;\n\t"
+            "addc.cc.u32 %2, %2, %17;\n\t"
+            "addc.cc.u32 %3, %3, %18;\n\t"
+            "addc.cc.u32 %4, %4, %19;\n\t"
+            "addc.cc.u32 %5, %5, %20;\n\t"
+            "addc.cc.u32 %6, %6, %21;\n\t"
+            "addc.cc.u32 %7, %7, %22;\n\t"
+            "addc.cc.u32 %8, %8, %23;\n\t"
+            "addc.cc.u32 %9, %9, %24;\n\t"
+            "addc.cc.u32 %10, %10, %25;\n\t"
+            "addc.cc.u32 %11, %11, %26;\n\t"
+            "addc.cc.u32 %12, %12, %27;\n\t"
+            "addc.cc.u32 %13, %13, %28;\n\t"
+            "addc.u32 %14, %14, %29;"
+            : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(Y[8]), "+r"(Y[9]),
+              "+r"(Y[10]), "+r"(Y[11]), "+r"(Y[12]), "+r"(Y[13]), "+r"(Y[14])
+            : "r"(Y1[0]), "r"(Y1[1]), "r"(Y1[2]), "r"(Y1[3]), "r"(Y1[4]), "r"(Y1[5]), "r"(Y1[6]), "r"(Y1[7]), "r"(Y1[8]), "r"(Y1[9]),
+              "r"(Y1[10]), "r"(Y1[11]), "r"(Y1[12]), "r"(Y1[13]), "r"(Y1[14]));
+    }
+    // a0 b0 + a1 b1 (+ a2 b2) in Montgomery form; pass n = 2 or 3
+    static __device__ __forceinline__ fe dot_ptx2(const fe &a0, const fe &b0, const fe &a1, const fe &b1, const fe &a2, const fe &b2, int n) {
+        uint32_t X[17], Y[17], X1[17], Y1[17];
+        mul_xy(X, Y, a0, b0);
+        mul_xy(X1, Y1, a1, b1);
+        xy_add(X, Y, X1, Y1);
+        if (n == 3) {
+            mul_xy(X1, Y1, a2, b2);
+            xy_add(X, Y, X1, Y1);
         }
         return redc2(X, Y);
     }
@@ -599,6 +662,21 @@ struct Fd {
         return mul_ptx2(a, b);
 #else
         return mul_portable(a, b);
+#endif
+    }
+    // a0 b0 + a1 b1 + a2 b2 with one reduction (device: lazy reduction; host: three products)
+    PASTA_HD static fe dot3(const fe &a0, const fe &b0, const fe &a1, const fe &b1, const fe &a2, const fe &b2) {
+#ifdef __CUDA_ARCH__
+        return dot_ptx2(a0, b0, a1, b1, a2, b2, 3);
+#else
+        return add_portable(add_portable(mul_portable(a0, b0), mul_portable(a1, b1)), mul_portable(a2, b2));
+#endif
+    }
+    PASTA_HD static fe dot2(const fe &a0, const fe &b0, const fe &a1, const fe &b1) {
+#ifdef __CUDA_ARCH__
+        return dot_ptx2(a0, b0, a1, b1, a1, b1, 2);
+#else
+        return add_portable(mul_portable(a0, b0), mul_portable(a1, b1));
 #endif
     }
     PASTA_HD static fe sqr(const fe &a) {

@@ -128,7 +128,21 @@ __global__ void __launch_bounds__(128) k_bpoly_combine(const fe *__restrict__ ta
     fe acc[COMBINE_ITEMS];
 #pragma unroll
     for (int e = 0; e < COMBINE_ITEMS; e++) acc[e] = fe_zero();
-    for (uint32_t j = begin; j < end; j++) {
+    // three proofs per step: the three products of a coefficient are summed unreduced and reduced ONCE (Fd::dot3,
+    // fe.cuh: p^2 / 2^256 < p / 4, so the sum still reduces below 2 p) -- a quarter fewer multiply-pipe instructions
+    uint32_t j = begin;
+    for (; j + 3 <= end; j += 3) {
+        const fe *t0 = tables + (size_t)(subset ? subset[j] : j) * BPOLY_TABLE;
+        const fe *t1 = tables + (size_t)(subset ? subset[j + 1] : j + 1) * BPOLY_TABLE;
+        const fe *t2 = tables + (size_t)(subset ? subset[j + 2] : j + 2) * BPOLY_TABLE;
+        const fe lo0 = t0[il], lo1 = t1[il], lo2 = t2[il];
+#pragma unroll
+        for (int e = 0; e < COMBINE_ITEMS; e++) {
+            if (ih0 + e < n_hi)
+                acc[e] = Fd<S>::add(acc[e], Fd<S>::dot3(t0[256u + ih0 + e], lo0, t1[256u + ih0 + e], lo1, t2[256u + ih0 + e], lo2));
+        }
+    }
+    for (; j < end; j++) {
         const fe *t = tables + (size_t)(subset ? subset[j] : j) * BPOLY_TABLE;
         fe lo = t[il];
 #pragma unroll

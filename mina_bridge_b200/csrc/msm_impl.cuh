@@ -249,6 +249,11 @@ template <class F>
 __device__ __noinline__ fe sqr_call(const fe a) {
     return Fd<F>::sqr(a);
 }
+// a0 b0 + a1 b1 with ONE reduction (Fd::dot2): Y3 of the mixed addition is a difference of two products
+template <class F>
+__device__ __noinline__ fe dot2_call(const fe a0, const fe b0, const fe a1, const fe b1) {
+    return Fd<F>::dot2(a0, b0, a1, b1);
+}
 // Ec<F>::add_mixed with the multiplications out of line (same formulas, "madd-2008-s")
 template <class F>
 __device__ __forceinline__ void add_mixed_compact(xyzz &p, const affine &q) {
@@ -273,7 +278,7 @@ __device__ __forceinline__ void add_mixed_compact(xyzz &p, const affine &q) {
     fe PPP = mul_call<F>(P, PP);
     fe Q = mul_call<F>(p.x, PP);
     fe X3 = fd::sub(fd::sub(sqr_call<F>(R), PPP), fd::dbl(Q));
-    fe Y3 = fd::sub(mul_call<F>(R, fd::sub(Q, X3)), mul_call<F>(p.y, PPP));
+    fe Y3 = dot2_call<F>(R, fd::sub(Q, X3), fd::neg(p.y), PPP);
     p.x = X3;
     p.y = Y3;
     p.zz = mul_call<F>(p.zz, PP);

@@ -27,12 +27,8 @@ __device__ __forceinline__ void poseidon_permute(const fe *__restrict__ tab, fe 
             sb[i] = Fd<F>::mul(Fd<F>::mul(x4, x2), st[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            fe acc = Fd<F>::mul(tab[3 * i], sb[0]);
-            acc = Fd<F>::add(acc, Fd<F>::mul(tab[3 * i + 1], sb[1]));
-            acc = Fd<F>::add(acc, Fd<F>::mul(tab[3 * i + 2], sb[2]));
-            st[i] = Fd<F>::add(acc, tab[9 + 3 * r + i]);
-        }
+        for (int i = 0; i < 3; i++)  // one MDS row = one dot product with a single reduction (Fd::dot3)
+            st[i] = Fd<F>::add(Fd<F>::dot3(tab[3 * i], sb[0], tab[3 * i + 1], sb[1], tab[3 * i + 2], sb[2]), tab[9 + 3 * r + i]);
     }
 }
 
@@ -61,10 +57,7 @@ struct LaneSponge {
             fe x2 = Fd<F>::sqr(st), x4 = Fd<F>::sqr(x2);
             fe sb = Fd<F>::mul(Fd<F>::mul(x4, x2), st);
             fe s0 = from_lane(sb, 0), s1 = from_lane(sb, 1), s2 = from_lane(sb, 2);
-            fe acc = Fd<F>::mul(tab[3 * row], s0);
-            acc = Fd<F>::add(acc, Fd<F>::mul(tab[3 * row + 1], s1));
-            acc = Fd<F>::add(acc, Fd<F>::mul(tab[3 * row + 2], s2));
-            st = Fd<F>::add(acc, tab[9 + 3 * r + row]);
+            st = Fd<F>::add(Fd<F>::dot3(tab[3 * row], s0, tab[3 * row + 1], s1, tab[3 * row + 2], s2), tab[9 + 3 * r + row]);
         }
     }
     // x: Montgomery, the same value on every lane of the group

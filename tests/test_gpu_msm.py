@@ -54,6 +54,18 @@ def test_both_device_multipliers_match_the_portable_product(gpu):
         assert gpu.field_op(fid, 16, A, B) == want
         assert gpu.field_op(fid, 17, A, B) == want
         assert gpu.field_op(fid, 10, A, B) == want
+        # sums of two / three products with ONE reduction (lazy reduction, Fd::dot2 / Fd::dot3): the worst case is
+        # three products of values near p, which is what the tail of `vals` reversed against itself provides
+        n = len(a)
+        p2 = [(a[i] * b[i] + a[(i + 1) % n] * b[(i + 1) % n]) * rinv % m for i in range(n)]
+        p3 = [(a[i] * b[i] + a[(i + 1) % n] * b[(i + 1) % n] + a[(i + 2) % n] * b[(i + 2) % n]) * rinv % m for i in range(n)]
+        assert gpu.field_op(fid, 18, A, B) == cref.ints_to_bytes(p2)
+        assert gpu.field_op(fid, 19, A, B) == cref.ints_to_bytes(p3)
+        big = [m - 1, m - 2, m - 3, m - 1, m - 5, m - 1]
+        Bg = cref.ints_to_bytes(big)
+        nb = len(big)
+        assert gpu.field_op(fid, 19, Bg, Bg) == cref.ints_to_bytes(
+            [(big[i] ** 2 + big[(i + 1) % nb] ** 2 + big[(i + 2) % nb] ** 2) * rinv % m for i in range(nb)])
         # dedicated squaring (op 4 converts in and out of Montgomery form around Fd::sqr)
         assert gpu.field_op(fid, 4, A) == cref.ints_to_bytes([x * x % m for x in a])
 
