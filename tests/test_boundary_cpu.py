@@ -433,3 +433,24 @@ def test_poseidon_reference_kat(mb):
     assert oposeidon.merkle_root(table, 0, [(0, 0), (1, 0)], pasta.P) == oposeidon.KAT_ROOT
     h0 = mb.host_hash_with_kimchi(tb, "MinaMklTree000", [0, 0])
     assert mb.host_hash_with_kimchi(tb, "MinaMklTree001", [0, h0]) == oposeidon.KAT_ROOT
+
+
+def test_poseidon_table_tool_refuses_a_table_that_fails_the_kat(mb, tmp_path):
+    """tools/make_poseidon_table.py is the one door through which constants enter the library: it must extract 9 + 165
+    literals in order, reject a wrong field, and never write a table that fails merkle_verifier.rs:43-58."""
+    import sys
+
+    rng = random.Random(11)
+    nums = [rng.randrange(10 ** 70, pasta.P) for _ in range(174)]
+    src = tmp_path / "fp_kimchi.rs"
+    src.write_text("\n".join('Fp::from_str("%d").unwrap(), // 0x%064x' % (x, 7) if i % 2 else "field_from_hex(\"0x%064x\")" % x for i, x in enumerate(nums)))
+    tool = os.path.join(ROOT, "tools", "make_poseidon_table.py")
+    out = os.path.join(ROOT, "mina_bridge_b200", "data", "poseidon_fp_kimchi.bin")
+    existed = os.path.exists(out)
+    r = subprocess.run([sys.executable, tool, "fp", str(src)], capture_output=True, text=True)
+    assert r.returncode != 0 and "KAT" in (r.stdout + r.stderr)
+    assert os.path.exists(out) == existed  # nothing was written
+    # literals of the other field's size are refused before the KAT
+    src.write_text("\n".join('"%d"' % (pasta.Q - 1 - i) for i in range(174)))
+    r = subprocess.run([sys.executable, tool, "fp", str(src)], capture_output=True, text=True)
+    assert r.returncode != 0 and "canonical" in (r.stdout + r.stderr)
