@@ -1000,20 +1000,99 @@ static void state_host_pass(StateJob &j) {
     }
 }
 
+// Host passes (bincode decode, on-curve checks, packing) run on a persistent pool: spawning 16 threads per batch cost
+// about as much as decoding it.  One batch at a time uses the pool; a second concurrent caller (rare: the coalescer
+// already merges callers) falls back to its own short-lived threads.  Exceptions are carried back to the caller.
+class HostPool {
+   public:
+    static HostPool &get() {
+        static HostPool *p = new HostPool;  // never destroyed: its detached workers outlive static destruction
+        return *p;
+    }
+    bool try_run(size_t n, const std::function<void(size_t)> &fn) {
+        std::unique_lock<std::mutex> own(owner_, std::try_to_lock);
+        if (!own.owns_lock() || workers_.empty()) return false;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            pending_ = workers_.size();
+            err_ = nullptr;
+            generation_++;
+        }
+        cv_.notify_all();
+        work();  // the caller takes its share
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+        if (err_) std::rethrow_exception(err_);
+        return true;
+    }
+
+   private:
+    HostPool() {
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned nw = std::min(hw, 32u);
+        for (unsigned t = 1; t < nw; t++) workers_.emplace_back([this] { loop(); });
+        for (auto &w : workers_) w.detach();  // process-lifetime workers
+    }
+    void work() {
+        try {
+            for (size_t i; (i = next_.fetch_add(1)) < n_;) (*fn_)(i);
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(m_);
+            if (!err_) err_ = std::current_exception();
+            next_.store(n_);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+            }
+            work();
+            std::lock_guard<std::mutex> lk(m_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::mutex owner_, m_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t n_ = 0, pending_ = 0;
+    std::atomic<size_t> next_{0};
+    uint64_t generation_ = 0;
+    std::exception_ptr err_;
+};
+
 static void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
-    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    size_t nthreads = std::min<size_t>(hw, (n + 3) / 4);
-    if (nthreads <= 1) {
+    if (n < 8) {
         for (size_t i = 0; i < n; i++) fn(i);
         return;
     }
+    if (HostPool::get().try_run(n, fn)) return;
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    size_t nthreads = std::min<size_t>(hw, (n + 3) / 4);
     std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex em;
     std::vector<std::thread> pool;
     for (size_t t = 0; t < nthreads; t++)
         pool.emplace_back([&]() {
-            for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+            try {
+                for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(em);
+                if (!err) err = std::current_exception();
+                next.store(n);
+            }
         });
     for (auto &th : pool) th.join();
+    if (err) std::rethrow_exception(err);
 }
 
 // `accumulators_only`: skip the pub-input / consensus stages (mina_b200_accumulator_check*)
