@@ -629,6 +629,7 @@ static void combine_slices(Context &c, AccRun &rs, SideBuffers &sb, const Accumu
 
 static void rlc_levels(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch &ab, RlcBatch &rb, const fe *d_chal, fe *d_r,
                        const uint32_t *h_bad);
+static constexpr uint32_t EAGER_LOCATOR_MAX = 256;  // batches up to this size compute the locator sums from level 0 on
 static void rlc_buffers(SideBuffers &sb, const AccumulatorBatch &ab, RlcBatch &rb) {
     rb.n_slices0 = (ab.m + COMBINE_SLICE - 1) / COMBINE_SLICE;
     rb.d_tab = sb.d_tab.reserve(2 * (size_t)ab.m * BPOLY_TABLE);
@@ -678,9 +679,32 @@ static void rlc_levels(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch
     c.launches += 1;
     combine_slices(c, rs, sb, ab, rb.d_tab, rb.d_partial, rb.n_slices0);
 
+    // The locator-weighted twins of the tables, slices and points.  Built after a failed level 0 -- or at once for a
+    // small batch (a shard of a multi-GPU job), where they cost ~0.2 ms and save the whole extra level (~1.2 ms)
+    // whenever something is bad.
+    auto build_weighted = [&]() {
+        if (rb.materialize) rb.materialize();  // per-item P_j that level 0 did without
+        CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));
+        CTX_CUDA_OK(cudaStreamWaitEvent(rs.aux, rs.fork, 0));
+        if (ab.curve == 0) {
+            k_weight_points<FpParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(rb.d_scaled, ab.m, rb.d_scaled_w);
+            k_weight_scalars<FqParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_r, ab.m, d_r + ab.m);
+        } else {
+            k_weight_points<FqParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(rb.d_scaled, ab.m, rb.d_scaled_w);
+            k_weight_scalars<FpParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_r, ab.m, d_r + ab.m);
+        }
+        launch_bpoly_tables(field, d_chal, rb.d_tab_w, ab.m, ab.k, d_r + ab.m, false, rs.s);
+        c.launches += 3;
+        combine_slices(c, rs, sb, ab, rb.d_tab_w, rb.d_partial_w, rb.n_slices0);
+        rb.weighted = true;
+    };
     LevelPlan plan;
     plan.sliced.push_back(LevelGroup{0, ab.m, 0});
     bool locator = false;
+    if (ab.m <= EAGER_LOCATOR_MAX && !rb.materialize && !rb.d_D0) {
+        build_weighted();
+        locator = true;
+    }
     for (int level = 0; plan.size(); level++) {
         std::vector<uint32_t> status = acc_check_groups(c, rs, sb, ab, rb, plan, level, locator);
         // the stream has drained: the on-curve flag of the batch's points is on the host
@@ -692,20 +716,7 @@ static void rlc_levels(Context &c, AccRun &rs, SideBuffers &sb, AccumulatorBatch
                 return;
             }
             // something is bad: build the locator-weighted twins once, then test the whole batch again with both sums
-            if (rb.materialize) rb.materialize();  // per-item P_j that level 0 did without
-            CTX_CUDA_OK(cudaEventRecord(rs.fork, rs.s));
-            CTX_CUDA_OK(cudaStreamWaitEvent(rs.aux, rs.fork, 0));
-            if (ab.curve == 0) {
-                k_weight_points<FpParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(rb.d_scaled, ab.m, rb.d_scaled_w);
-                k_weight_scalars<FqParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_r, ab.m, d_r + ab.m);
-            } else {
-                k_weight_points<FqParams><<<(ab.m + 63) / 64, 64, 0, rs.aux>>>(rb.d_scaled, ab.m, rb.d_scaled_w);
-                k_weight_scalars<FpParams><<<(ab.m + 127) / 128, 128, 0, rs.s>>>(d_r, ab.m, d_r + ab.m);
-            }
-            launch_bpoly_tables(field, d_chal, rb.d_tab_w, ab.m, ab.k, d_r + ab.m, false, rs.s);
-            c.launches += 3;
-            combine_slices(c, rs, sb, ab, rb.d_tab_w, rb.d_partial_w, rb.n_slices0);
-            rb.weighted = true;
+            build_weighted();
             locator = true;
             next.sliced.push_back(LevelGroup{0, ab.m, 0});
             plan = std::move(next);
