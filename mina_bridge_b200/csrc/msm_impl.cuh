@@ -568,8 +568,50 @@ __global__ void __launch_bounds__(32) k_bit_sums(const xyzz *__restrict__ last, 
 // tree) and unwinding of the running-sum passes.  Valid in lane 0.
 //   pass l turned points B with weights (b+1) into S (weights t) and W:  sum = sum W + m_l * sum_t t*S_t
 //   below the last pass the weights are t, above it they are (t+1):  D_l = sumW_l + m_l * (D_{l+1} - T).
+// s * p for a small non-negative scalar (binary method; a power of two costs only its doublings)
+template <class F>
+__device__ __forceinline__ xyzz small_scalar_mul(const xyzz &p, uint64_t s) {
+    xyzz acc = Ec<F>::identity();
+    if (s == 0) return acc;
+#pragma unroll 1
+    for (int b = 63 - __clzll((long long)s); b >= 0; b--) {
+        acc = Ec<F>::dbl(acc);
+        if ((s >> b) & 1ull) Ec<F>::add(acc, p);
+    }
+    return acc;
+}
+// Unwound, the result of a group is ONE linear combination of its slots with small coefficients:
+//   D = sum_k 2^k M_L U_k  +  sum_l M_l (sum of W^l partials)  -  (M_1 + .. + M_{L-1}) T      (L >= 1;  M_l = m_0 .. m_{l-1})
+//   D = sum_k 2^k U_k + T                                                                      (L == 0)
+// With at most 32 slots every lane scales its own slot (the deepest does nbits + log2 M_L doublings) and one shuffle
+// tree adds them: ~95 us instead of ~150 us for the level-by-level version below.
+template <class F>
+__device__ __forceinline__ xyzz group_result_flat(const xyzz *__restrict__ base, const TailParams &tp, uint32_t lane) {
+    int sh[MAX_LEVELS + 1];
+    sh[0] = 0;
+    for (int l = 0; l < tp.L; l++) sh[l + 1] = sh[l] + tp.log_m[l];
+    uint64_t coef = 0;
+    bool negate = false;
+    if (lane < (uint32_t)tp.nbits) {
+        coef = 1ull << (lane + sh[tp.L]);
+    } else if (lane < (uint32_t)tp.nbits + tp.parts_last) {
+        if (tp.L == 0) {
+            coef = 1;
+        } else {
+            for (int l = 1; l < tp.L; l++) coef += 1ull << sh[l];
+            negate = true;
+        }
+    } else if (lane < tp.slots) {
+        for (int l = 0; l < tp.L; l++)
+            if (lane >= tp.w_slot[l]) coef = 1ull << sh[l];
+    }
+    xyzz V = (lane < tp.slots && coef) ? small_scalar_mul<F>(base[lane], coef) : Ec<F>::identity();
+    if (negate) V.y = Fd<F>::neg(V.y);
+    return warp_sum_points<F>(V);
+}
 template <class F>
 __device__ __forceinline__ xyzz group_result(const xyzz *__restrict__ base, const TailParams &tp, uint32_t lane) {
+    if (tp.slots <= 32 && tp.nbits + (tp.L ? tp.log_m[0] * tp.L : 0) < 60) return group_result_flat<F>(base, tp, lane);
     xyzz V = lane < (uint32_t)tp.nbits ? base[lane] : Ec<F>::identity();
     for (uint32_t k = 0; k < lane && lane < (uint32_t)tp.nbits; k++) V = Ec<F>::dbl(V);
     xyzz D = warp_sum_points<F>(V);  // Z = sum_t t * B_t
