@@ -84,6 +84,10 @@ int mina_b200_fixed_base_msm_device(int curve, uint32_t nmsm, const void *d_scal
  * resident SRS (kimchi `SRS::add_lagrange_basis`, AL/operator/mina/lib/src/verifier_index.rs:204-208; the verifier's
  * public-input commitment is -sum_i pub_i L_i + h over the first `public` = 40 of them).  2^log_n <= SRS depth. */
 int mina_b200_lagrange_commitments(int curve, uint32_t log_n, uint32_t first, uint32_t count, uint8_t *out64);
+/* kimchi's public-input commitment (`public_comm` in kimchi's verifier; part of SURVEY row a8) for nproofs vectors of
+ * n_pub public inputs (pub32: [nproofs][n_pub] canonical scalars): out = -sum_i pub_i L_i + h.  The Lagrange commitments
+ * are computed once per (log_n, n_pub) and kept as a small fixed-base table. */
+int mina_b200_public_commitments(int curve, uint32_t log_n, uint32_t n_pub, uint32_t nproofs, const uint8_t *pub32, uint8_t *out64);
 /* MSM engine tuning (takes effect at the next init / table rebuild): window bits and running-sum
  * chunk.  Returns 0 on success. */
 int mina_b200_msm_configure(int curve, int window_bits, int precompute, int leaf);

@@ -137,6 +137,10 @@ static void destroy_device_state(Context &c) {
     for (int k = 0; k < 2; k++) {
         c.curve[k].fixed.reset();
         c.curve[k].var.reset();
+        c.curve[k].lagr.reset();
+        if (c.curve[k].d_lagr) cudaFree(c.curve[k].d_lagr);
+        c.curve[k].d_lagr = nullptr;
+        c.curve[k].lagr_n = c.curve[k].lagr_log_n = 0;
         c.curve[k].user.reset();
         if (c.curve[k].d_user) cudaFree(c.curve[k].d_user);
         c.curve[k].d_user = nullptr;
@@ -307,17 +311,11 @@ int mina_b200_msm_srs_device(int curve, uint32_t nmsm, uint32_t n, const void *d
     ABI_CATCH
 }
 
-int mina_b200_lagrange_commitments(int curve, uint32_t log_n, uint32_t first, uint32_t count, uint8_t *out64) {
-    ABI_TRY
-    require_ready();
-    if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
-    Context &c = ctx();
-    std::lock_guard<std::mutex> lk(c.mu);
-    CTX_CUDA_OK(cudaSetDevice(c.device));
+// device side of the Lagrange commitments: `count` Montgomery affine points into d_out (c.mu held)
+static void lagrange_commitments_device(Context &c, int curve, uint32_t log_n, uint32_t first, uint32_t count, affine *d_out) {
     CurveCtx &cc = c.curve[curve];
     if (log_n == 0 || log_n > 30 || (1u << log_n) > cc.depth) throw std::runtime_error("lagrange: domain larger than the resident SRS");
     if ((uint64_t)first + count > (1ull << log_n)) throw std::runtime_error("lagrange: index out of the domain");
-    if (!count) return 0;
     const int sfield = curve == 1 ? 0 : 1;
     fe omega_inv, n_inv;
     if (sfield == 0)
@@ -329,19 +327,96 @@ int mina_b200_lagrange_commitments(int curve, uint32_t log_n, uint32_t first, ui
     // rows of scalars in chunks of at most 64 commitments (64 x 2^14 x 32 B = 32 MiB)
     const uint32_t chunk = std::max<uint32_t>(1, std::min<uint32_t>(count, (1u << 20) / n ? (1u << 20) / n : 1));
     fe *d_sc = reinterpret_cast<fe *>(sc.scalars[0].reserve((size_t)chunk * n * 8));
-    affine *out = sc.out.reserve(chunk);
-    uint32_t *can = sc.out_can.reserve((size_t)chunk * 16);
     cc.fixed->enable_kernel_timing(false);
     for (uint32_t done = 0; done < count; done += chunk) {
         const uint32_t cur = std::min(chunk, count - done);
         launch_lagrange_scalars(sfield, omega_inv, n_inv, (int)log_n, first + done, cur, d_sc, c.stream);
-        cc.fixed->run(reinterpret_cast<const uint32_t *>(d_sc), cur, n, out, c.stream);
-        launch_affine_from_mont(curve, out, can, cur, c.stream);
-        c.launches += 2;
-        CTX_CUDA_OK(cudaMemcpyAsync(out64 + 64 * (size_t)done, can, 64 * (size_t)cur, cudaMemcpyDeviceToHost, c.stream));
-        CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+        cc.fixed->run(reinterpret_cast<const uint32_t *>(d_sc), cur, n, d_out + done, c.stream);
+        c.launches += 1;
+        CTX_CUDA_OK(cudaStreamSynchronize(c.stream));  // d_sc is reused by the next chunk
     }
     if (cc.fixed->take_error(c.stream)) throw std::runtime_error("lagrange: scalar overflow flagged by the MSM engine");
+}
+
+int mina_b200_lagrange_commitments(int curve, uint32_t log_n, uint32_t first, uint32_t count, uint8_t *out64) {
+    ABI_TRY
+    require_ready();
+    if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    if (!count) return 0;
+    AbiScratch &sc = scratch();
+    affine *out = sc.out.reserve(count);
+    uint32_t *can = sc.out_can.reserve((size_t)count * 16);
+    lagrange_commitments_device(c, curve, log_n, first, count, out);
+    launch_affine_from_mont(curve, out, can, count, c.stream);
+    c.launches += 1;
+    CTX_CUDA_OK(cudaMemcpyAsync(out64, can, 64 * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+    ABI_CATCH
+}
+
+// kimchi's public-input commitment (verifier.rs `public_comm`): -sum_i pub_i L_i + h for nproofs vectors
+// of n_pub public inputs.  The n_pub Lagrange commitments and h form a small fixed base set (window table, c = 8).
+int mina_b200_public_commitments(int curve, uint32_t log_n, uint32_t n_pub, uint32_t nproofs, const uint8_t *pub32, uint8_t *out64) {
+    ABI_TRY
+    require_ready();
+    if (curve < 0 || curve > 1) throw std::runtime_error("bad curve id");
+    if (n_pub == 0 || n_pub > 4096) throw std::runtime_error("public_commitments: bad number of public inputs");
+    if (!nproofs) return 0;
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    CTX_CUDA_OK(cudaSetDevice(c.device));
+    CurveCtx &cc = c.curve[curve];
+    if (!cc.lagr || cc.lagr_n != n_pub || cc.lagr_log_n != log_n) {
+        cc.lagr.reset();
+        if (cc.d_lagr) cudaFree(cc.d_lagr);
+        cc.d_lagr = nullptr;
+        cc.lagr_n = cc.lagr_log_n = 0;
+        CTX_CUDA_OK(cudaMalloc(&cc.d_lagr, (size_t)(n_pub + 1) * sizeof(affine)));
+        lagrange_commitments_device(c, curve, log_n, 0, n_pub, cc.d_lagr);
+        CTX_CUDA_OK(cudaMemcpyAsync(cc.d_lagr + n_pub, cc.d_srs + cc.depth, sizeof(affine), cudaMemcpyDeviceToDevice, c.stream));  // h
+        MsmConfig cfg;
+        cfg.precompute = true;
+        cfg.c = 8;
+        cc.lagr.reset(make_msm_engine(curve));
+        cc.lagr->set_bases(cc.d_lagr, n_pub + 1, cfg, c.stream);
+        CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+        cc.lagr_n = n_pub;
+        cc.lagr_log_n = log_n;
+    }
+    // scalars: -pub_i (host, canonical) then 1 for h
+    const int sfield = curve == 1 ? 0 : 1;
+    std::vector<uint8_t> sc_host((size_t)nproofs * (n_pub + 1) * 32);
+    auto negate = [&](auto tag) {
+        using E = host::Fe<decltype(tag)>;
+        for (uint32_t p = 0; p < nproofs; p++) {
+            for (uint32_t i = 0; i < n_pub; i++) {
+                E x;
+                if (!E::from_bytes_le(pub32 + 32 * ((size_t)p * n_pub + i), x)) throw std::runtime_error("public_commitments: a public input is not canonical");
+                (-x).to_bytes_le(&sc_host[32 * ((size_t)p * (n_pub + 1) + i)]);
+            }
+            E::one().to_bytes_le(&sc_host[32 * ((size_t)p * (n_pub + 1) + n_pub)]);
+        }
+    };
+    if (sfield == 0)
+        negate(FpParams{});
+    else
+        negate(FqParams{});
+    AbiScratch &sc = scratch();
+    uint32_t *d_sc = sc.scalars[0].reserve((size_t)nproofs * (n_pub + 1) * 8);
+    affine *out = sc.out.reserve(nproofs);
+    uint32_t *can = sc.out_can.reserve((size_t)nproofs * 16);
+    CTX_CUDA_OK(cudaMemcpyAsync(d_sc, sc_host.data(), sc_host.size(), cudaMemcpyHostToDevice, c.stream));
+    cc.lagr->enable_kernel_timing(false);
+    cc.lagr->run(d_sc, nproofs, n_pub + 1, out, c.stream);
+    launch_affine_from_mont(curve, out, can, nproofs, c.stream);
+    c.launches += 1;
+    CTX_CUDA_OK(cudaMemcpyAsync(out64, can, 64 * (size_t)nproofs, cudaMemcpyDeviceToHost, c.stream));
+    CTX_CUDA_OK(cudaStreamSynchronize(c.stream));
+    if (cc.lagr->take_error(c.stream)) throw std::runtime_error("public_commitments: scalar overflow flagged by the MSM engine");
     return 0;
     ABI_CATCH
 }

@@ -39,6 +39,10 @@ struct CurveCtx {
     std::unique_ptr<MsmEngineBase> user;   // caller-supplied bases that stay resident (fixed-base table)
     affine *d_user = nullptr;
     uint32_t user_n = 0;
+    // public-input commitment: fixed-base engine over the first `lagr_n` Lagrange commitments of the 2^lagr_log_n domain + h
+    std::unique_ptr<MsmEngineBase> lagr;
+    affine *d_lagr = nullptr;
+    uint32_t lagr_n = 0, lagr_log_n = 0;
     MsmConfig cfg;
     std::vector<uint8_t> host_canonical;  // (depth + 1) x 64 bytes canonical, for tests / host logic
 };

@@ -69,6 +69,14 @@ def lagrange_commitments(curve: int, log_n: int, first: int, count: int) -> list
     return [out.raw[64 * i : 64 * i + 64] for i in range(count)]
 
 
+def public_commitments(curve: int, log_n: int, n_pub: int, pub: bytes) -> list[bytes]:
+    """-sum_i pub_i L_i + h for each vector of n_pub public inputs (canonical scalars)."""
+    nproofs = len(pub) // (32 * n_pub)
+    out = ctypes.create_string_buffer(64 * max(nproofs, 1))
+    _check(load().mina_b200_public_commitments(curve, ctypes.c_uint32(log_n), ctypes.c_uint32(n_pub), ctypes.c_uint32(nproofs), pub, out))
+    return [out.raw[64 * i : 64 * i + 64] for i in range(nproofs)]
+
+
 def msm_srs(curve: int, scalars: bytes, n: int) -> list[bytes]:
     """nmsm MSMs over the resident SRS prefix g[0..n); returns canonical affine results."""
     assert n == 0 or len(scalars) % (32 * n) == 0

@@ -216,3 +216,22 @@ def test_lagrange_commitments_match_the_oracle(gpu):
     # and the 40 the verifier uses come out in one call, equal to the single calls
     first40 = gpu.lagrange_commitments(0, log_n, 0, 40)
     assert first40[0] == got[0] and first40[1] == got[1] and first40[39] == got[2]
+
+
+def test_public_input_commitment_matches_the_oracle(gpu):
+    """kimchi `public_comm` (part of a8): -sum_i pub_i L_i + h over the 40 Lagrange commitments of the wrap domain,
+    for a batch of public-input vectors incl. edge values, against the oracle MSM over the same bases."""
+    log_n, n_pub, q = 14, 40, pasta.Q
+    lag = gpu.lagrange_commitments(0, log_n, 0, n_pub)
+    h = gpu.srs_points(0, 0, 1, want_h=True)[1]
+    bases = b"".join(lag) + h
+    rng = random.Random(99)
+    vecs = [[rng.randrange(q) for _ in range(n_pub)] for _ in range(5)]
+    vecs.append([0] * n_pub)                      # all zero: the commitment is h itself
+    vecs.append([1] + [0] * (n_pub - 1))
+    vecs.append([q - 1] * n_pub)
+    got = gpu.public_commitments(0, log_n, n_pub, b"".join(cref.ints_to_bytes(v) for v in vecs))
+    for v, pt in zip(vecs, got):
+        want, inf = cref.msm(cref.FP, cref.ints_to_bytes([(-x) % q for x in v] + [1]), bases, 2)
+        assert not inf and pt == want
+    assert got[5] == h
