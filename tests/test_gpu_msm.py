@@ -160,6 +160,19 @@ def test_msm_generic_bases_windows(gpu, cid, c):
     assert gpu.msm(cid, sc, pts, c) == want
 
 
+@pytest.mark.parametrize("c", [2, 3, 4, 5, 6, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20])
+def test_msm_every_window_width(gpu, c):
+    """The reduction tail is planned per window width (running-sum passes, bit sums, partial sums, the flat and the
+    level-by-level finalize): every width from 2 to 20 must give the oracle's point, including the widths whose top
+    window only carries (c = 5, 15, 17) and the ones with more than 32 slots per group (c >= 17)."""
+    rng = random.Random(900 + c)
+    n = 257
+    pts = gpu.srs_points(1, 7, n)
+    sc = rand_scalars(rng, n - 3, SCALAR_MOD[1]) + cref.ints_to_bytes([SCALAR_MOD[1] - 1, 1, 0])
+    want, _ = cref.msm(1, sc, pts, 2)
+    assert gpu.msm(1, sc, pts, c) == want
+
+
 def test_accumulator_kats_on_gpu(gpu, state_proof):
     # K-A, K-B, K-C with ORACLE-prepared scalars: pins the MSM engine alone.  The full row (device endo +
     # b_poly + MSM from raw proof bytes) is tests/test_gpu_verifier.py::test_accumulator_check_*.
